@@ -1,0 +1,340 @@
+"""Shared machinery behind the model contract.
+
+The reference duplicates ~300 lines of iteration protocol in every model file
+(``alex_net.py:300-585``, ``googlenet.py:650-950``, ``cifar10.py:254-493`` …): shared
+input buffers + sub-batch slicing, the loader handshake, ``train_iter`` / ``val_iter``
+/ ``reset_iter`` / ``adjust_hyperp`` / ``cleanup`` and the compile helpers.
+:class:`ModelBase` implements that protocol once; a concrete model only provides
+hyper-parameters, its data object and ``build_model()`` / ``forward()``.
+
+Contract exposed (ref ``helper_funcs.py:163-205``, ``README.md:54-67``):
+``params`` (list of torch tensors — views into the flat arena), ``data``,
+``compile_iter_fns(sync_type)``, ``train_iter(count, recorder)``,
+``val_iter(count, recorder)``, ``reset_iter(mode)``, ``adjust_hyperp(epoch)``,
+``cleanup()``, ``n_epochs``, ``epoch``, ``n_subb``; plus ``vels``/``vels2``,
+``shared_lr``, ``get_vel``/``descent_vel``/``train_iter_fn``/``val_iter_fn``.
+
+B200-native pieces: bf16 NHWC activations with fp32 master weights in the arena;
+the whole step (H2D hand-off excluded) can be captured in a CUDA graph
+(``config['cuda_graph']``); lr/momentum live in device memory so the graph never
+needs re-capture; costs/errors stay on the device until the recorder prints.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+import torch
+
+from .. import ops
+from ..parallel.arena import FlatArena
+from ..utils.opt import FlatSGD, SharedScalar, pre_model_iter_fn
+from .layers2 import Crop, Dropout, count_params
+
+
+def pick_device(config):
+    dev = config.get("device")
+    if dev is not None:
+        return torch.device(dev)
+    if torch.cuda.is_available():
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+class ModelBase(object):
+    # ---- hyper-parameter defaults (override per model)
+    n_epochs = 1
+    momentum = 0.9
+    weight_decay = 0.0
+    batch_size = 128
+    file_batch_size = 128
+    learning_rate = 0.01
+    lr_policy = "step"
+    lr_step = ()
+    lr_gamma = 0.1
+    use_momentum = True
+    use_nesterov_momentum = False
+    input_width = 227
+    input_height = 227
+    batch_crop_mirror = False
+    rand_crop = True
+    monitor_grad = False
+    name = "Model"
+
+    def __init__(self, config):
+        self.config = config
+        self.verbose = config.get("verbose", False)
+        self.rank = config.get("rank", 0)
+        self.size = config.get("size", 1)
+        self.no_paraload = config.get("no_paraload", False)
+        self.device = pick_device(config)
+        self.cuda = self.device.type == "cuda"
+        self.act_dtype = torch.bfloat16 if self.cuda else torch.float32
+        self.use_graph = bool(config.get("cuda_graph", False)) and self.cuda
+        self.epoch = 0
+        self.step_idx = 0
+        self.mu = self.momentum
+        self.eta = self.weight_decay
+        self.base_lr = np.float32(self.learning_rate)
+        self.current_t = self.subb_t = 0
+        self.current_v = self.subb_v = 0
+        self.last_one_t = self.last_one_v = False
+        self.compiled_train_fn_list = []
+        self.train_iter_fn = None
+        self.val_iter_fn = None
+        self._graph = None
+        self._graph_out = None
+        self._warm = 0
+        self._tail = None
+        self.exchanger = None          # set by the BSP worker for fused / overlapped exchange
+        self.h2d_bytes_last = 0
+
+    # ------------------------------------------------------------------ construction helpers
+    def setup_data_parallel(self, data):
+        """The 'mini batching and other data parallel common routine' block of every
+        reference model (``alex_net.py:73-80``)."""
+        self.data = data
+        data.batch_data(self.file_batch_size)
+        data.extend_data(rank=self.rank, size=self.size)
+        data.shuffle_data(mode="train", common_seed=1234)
+        data.shuffle_data(mode="val")
+        data.shard_data(mode="train", rank=self.rank, size=self.size)
+        data.shard_data(mode="val", rank=self.rank, size=self.size)
+        self.n_subb = max(1, self.file_batch_size // self.batch_size)
+
+    def finalize(self, params, weight_types, input_shape):
+        """Bind parameters into the flat arena and allocate the shared input buffers."""
+        self.params, self.weight_types = list(params), list(weight_types)
+        count_params(self.params, verbose=False)
+        allocator = self.config.get("arena_allocator")
+        self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta,
+                               with_recv=False, allocator=allocator)
+        self.shared_lr = SharedScalar(self.arena.hyper, 0, self.base_lr)
+        self.sgd = FlatSGD(self.arena, self.mu, self.use_nesterov_momentum, self.use_momentum)
+        B = self.batch_size
+        fb = self.file_batch_size
+        self.input_shape = tuple(input_shape)           # (B, H, W, C)
+        self.shared_x = torch.zeros((fb,) + self.input_shape[1:], dtype=self.act_dtype, device=self.device)
+        self.shared_y = torch.zeros((fb,), dtype=torch.int64, device=self.device)
+        self.x_in = torch.zeros((B,) + self.input_shape[1:], dtype=self.act_dtype, device=self.device)
+        self.y_in = torch.zeros((B,), dtype=torch.int64, device=self.device)
+        self._y_pinned = torch.zeros((fb,), dtype=torch.int64, pin_memory=self.cuda)
+        self.vels, self.vels2 = [], []
+        if self.verbose:
+            print("%s: %d tensors, %.3f M params, arena %.1f MiB on %s"
+                  % (self.name, len(self.params), self.arena.n_real / 1e6,
+                     self.arena.nbytes / 2 ** 20, self.device))
+
+    # ------------------------------------------------------------------ to be provided by the model
+    def build_model(self):
+        raise NotImplementedError
+
+    def forward(self, x):
+        """Return logits-layer output; must leave ``self.output_layer`` evaluated."""
+        raise NotImplementedError
+
+    def loss(self, x, y):
+        self.forward(x)
+        sm = self.output_layer
+        return sm.negative_log_likelihood(y), sm.errors(y), sm.errors_top_x(y)
+
+    # ------------------------------------------------------------------ step functions
+    def _fwd_bwd_eager(self):
+        cost, err, err5 = self.loss(self.x_in, self.y_in)
+        cost.backward()
+        return cost.detach(), err.detach()
+
+    def forward_backward(self, subb_ind=0):
+        """Forward + backward on sub-batch ``subb_ind`` of the shared input buffer;
+        gradients land in the arena's G region.  Returns device scalars (cost, error)."""
+        B = self.batch_size
+        if self.n_subb == 1 and self.shared_x.shape[0] == B:
+            self.x_in.copy_(self.shared_x, non_blocking=True)
+            self.y_in.copy_(self.shared_y, non_blocking=True)
+        else:
+            self.x_in.copy_(self.shared_x[subb_ind * B:(subb_ind + 1) * B], non_blocking=True)
+            self.y_in.copy_(self.shared_y[subb_ind * B:(subb_ind + 1) * B], non_blocking=True)
+        if not self.use_graph:
+            return self._step_body()
+        if self._graph is None:
+            if self._warm < 2:                       # eager warm-up before capture
+                self._warm += 1
+                return self._step_body()
+            self._capture()
+        self._graph.replay()
+        return self._graph_out
+
+    def _step_body(self):
+        out = self._fwd_bwd_eager()
+        if self._tail is not None:
+            with torch.no_grad():
+                self._tail()
+        self._after_step()
+        return out
+
+    def _after_step(self):
+        if self.cuda:
+            from ..ops import cuda_impl
+            cuda_impl.advance_step(self.device)
+        else:
+            ops.advance_rng_step()
+
+    def _capture(self):
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                out = self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        self._graph, self._graph_out = g, out
+
+    def set_step_tail(self, fn):
+        """Register work that runs right after backward as part of the step — and
+        therefore *inside* the captured CUDA graph: the local fused SGD (k = 1) or the
+        fused allreduce+SGD exchange kernels (k > 1)."""
+        self._tail = fn
+        self._graph = None
+        self._warm = 0
+
+    def compile_val(self):
+        def val_fn(subb_ind=0):
+            B = self.batch_size
+            x = self.shared_x[subb_ind * B:(subb_ind + 1) * B]
+            y = self.shared_y[subb_ind * B:(subb_ind + 1) * B]
+            with torch.no_grad():
+                c, e, e5 = self.loss(x, y)
+            return c, e, e5
+        self.val_fn = val_fn
+
+    def compile_inference(self):
+        def inf_fn(x):
+            with torch.no_grad():
+                Dropout.SetDropoutOff(); Crop.SetRandCropOff()
+                out = torch.softmax(self.forward(x).float(), dim=1)
+                Dropout.SetDropoutOn(); Crop.SetRandCropOn()
+            return out
+        self.inf_fn = inf_fn
+
+    def compile_train(self, *args):
+        self.compiled_train_fn_list.extend(args)
+
+    def compile_iter_fns(self, sync_type="avg", aggregate="momentum"):
+        """``sync_type='cdd'``: split step (get_vel / exchange / descent_vel);
+        ``'avg'``: self-contained local update (k = 1), the exchanger then averages
+        weights.  Fixes SURVEY §2.9 #5/#7: every model accepts ``sync_type`` and 'avg'
+        really updates."""
+        start = time.time()
+        self.sync_type = sync_type
+        k = self.size if sync_type == "cdd" else 1
+        if k > 1:
+            _ = self.arena.R                      # allocate the receive region
+        pre_model_iter_fn(self, k, aggregate=aggregate)
+        if self.verbose:
+            print("Compile time: %.3f s" % (time.time() - start))
+
+    # ------------------------------------------------------------------ data movement
+    def _labels_to_device(self, labels):
+        n = len(labels)
+        self._y_pinned[:n] = torch.as_tensor(np.asarray(labels, dtype=np.int64))
+        self.shared_y[:n].copy_(self._y_pinned[:n], non_blocking=True)
+        return n * 8
+
+    def _load_file_batch(self, mode, idx, img, labels, n_batches):
+        """Loader handshake (ref ``alex_net.py:394-448``): request the next file,
+        wait for the current one, put labels on the device."""
+        loader = getattr(self.data, "loader", None)
+        last = idx == n_batches - 1
+        nbytes = 0
+        if loader is not None:
+            if idx == 0:
+                loader.set_mode(mode)
+                loader.request(img[idx], mode)
+            loader.request(img[idx + 1] if not last else img[idx], mode)
+            b = loader.get()
+            self.shared_x = b.x
+            nbytes += b.h2d_bytes
+        else:
+            x = self.data.load_batch(img[idx], mode, self)
+            self.shared_x[:x.shape[0]].copy_(x.to(self.act_dtype), non_blocking=True)
+            nbytes += x.numel() * x.element_size()
+        nbytes += self._labels_to_device(labels[idx])
+        self.h2d_bytes_last = nbytes
+        return last
+
+    # ------------------------------------------------------------------ the contract
+    def reset_iter(self, mode):
+        if mode == "train":
+            self.current_t = self.subb_t = 0
+            self.last_one_t = False
+        else:
+            self.current_v = self.subb_v = 0
+            self.last_one_v = False
+        loader = getattr(self.data, "loader", None)
+        if loader is not None:
+            loader.drain()       # the one look-ahead request issued for the last file
+
+    def train_iter(self, count, recorder):
+        if self.current_t == 0 and self.subb_t == 0:
+            self.data.shuffle_data(mode="train", common_seed=self.epoch)
+            self.data.shard_data(mode="train", rank=self.rank, size=self.size)
+        img, labels = self.data.train_img_shard, self.data.train_labels_shard
+        if self.subb_t == 0:
+            recorder.start()
+            self.last_one_t = self._load_file_batch("train", self.current_t, img, labels,
+                                                    self.data.n_batch_train)
+            recorder.end("wait")
+        recorder.start()
+        cost, error = self.train_iter_fn(self.subb_t)
+        recorder.train_error(count, cost, error)
+        recorder.end("calc")
+        if self.monitor_grad and self.verbose:
+            print(self.grad_norms())
+        if (self.subb_t + 1) // self.n_subb == 1:
+            self.current_t = 0 if self.last_one_t else self.current_t + 1
+            self.subb_t = 0
+        else:
+            self.subb_t += 1
+        self.step_idx += 1
+
+    def val_iter(self, count, recorder):
+        if self.current_v == 0 and self.subb_v == 0:
+            self.data.shuffle_data(mode="val")
+            self.data.shard_data(mode="val", rank=self.rank, size=self.size)
+        img, labels = self.data.val_img_shard, self.data.val_labels_shard
+        if self.subb_v == 0:
+            self.last_one_v = self._load_file_batch("val", self.current_v, img, labels,
+                                                    self.data.n_batch_val)
+        Dropout.SetDropoutOff(); Crop.SetRandCropOff()
+        cost, error, error_top5 = self.val_iter_fn(self.subb_v)
+        Dropout.SetDropoutOn(); Crop.SetRandCropOn()
+        recorder.val_error(count, cost, error, error_top5)
+        if (self.subb_v + 1) // self.n_subb == 1:
+            self.current_v = 0 if self.last_one_v else self.current_v + 1
+            self.subb_v = 0
+        else:
+            self.subb_v += 1
+
+    def adjust_hyperp(self, epoch):
+        """Once per epoch (ref ``alex_net.py:569-579``, ``googlenet.py:925-945``)."""
+        if self.lr_policy == "step":
+            if epoch in self.lr_step:
+                self.shared_lr.set_value(np.float32(self.shared_lr.get_value() * self.lr_gamma))
+        elif self.lr_policy == "poly":
+            power = getattr(self, "lr_power", 0.5)
+            self.shared_lr.set_value(np.float32(self.base_lr * (1.0 - float(epoch + 1) / self.n_epochs) ** power))
+        elif self.lr_policy == "auto":
+            pass
+
+    def scale_lr(self, size):
+        self.shared_lr.set_value(np.float32(self.shared_lr.get_value() * size))
+
+    def grad_norms(self):
+        """L2 grad-norm monitor (ref ``alex_net.py:311-320``): (sum, max) of log10 norms."""
+        norms = torch.stack([g.float().norm() for g in self.arena.views("G")]).clamp_min(1e-30).log10()
+        return [float(norms.sum()), float(norms.max())]
+
+    def cleanup(self):
+        if getattr(self.data, "para_load", False) and hasattr(self.data, "para_load_close"):
+            self.data.para_load_close()

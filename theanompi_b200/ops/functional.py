@@ -1,0 +1,302 @@
+"""Autograd-aware functional ops.
+
+Each op dispatches on the device of its input:
+
+* CUDA  → :mod:`theanompi_b200.ops.cuda_impl` (hand-written sm_100a kernels from
+  ``csrc/``; hard error when the extension is missing),
+* CPU   → :mod:`theanompi_b200.ops.reference` (plain torch, fp32).
+
+Weight gradients do not travel through autograd's AccumulateGrad: when a
+parameter carries a ``gbuf`` attribute (a view into the flat gradient arena, see
+:class:`theanompi_b200.parallel.arena.FlatArena`) the backward kernel writes the
+fp32 gradient straight into it and then fires ``on_ready`` — that callback is
+what lets the BSP exchanger launch the fused allreduce+SGD kernel for a bucket
+on a side stream while backward is still running on the main stream
+(the reference is strictly sequential, ``theanompi/worker.py:94-97``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import reference as ref
+
+
+def _impl(x):
+    if x.is_cuda:
+        from . import cuda_impl
+        return cuda_impl
+    return ref
+
+
+def compute_weight(p):
+    """bf16 shadow of a master parameter when one exists (GPU), else itself."""
+    sh = getattr(p, "shadow", None)
+    return sh if sh is not None else p
+
+
+def _sink(p, grad):
+    """Deliver a parameter gradient. Returns what autograd should see."""
+    gbuf = getattr(p, "gbuf", None)
+    if gbuf is None:
+        return grad.to(p.dtype).view_as(p)
+    if grad is not None and grad.data_ptr() != gbuf.data_ptr():
+        if getattr(p, "gaccum", False):
+            gbuf.add_(grad.view_as(gbuf))
+        else:
+            gbuf.copy_(grad.view_as(gbuf))
+    cb = getattr(p, "on_ready", None)
+    if cb is not None:
+        cb(p)
+    return None
+
+
+def _gout(p):
+    """Output buffer the backward kernel may write the fp32 grad into directly."""
+    if getattr(p, "gaccum", False):
+        return None
+    return getattr(p, "gbuf", None)
+
+
+# --------------------------------------------------------------------------- linear
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        impl = _impl(x)
+        wc = compute_weight(w)
+        y = impl.linear_bias_act(x, wc, b, relu)
+        ctx.save_for_backward(x, y)
+        ctx.w, ctx.b, ctx.relu = w, b, relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        impl = _impl(x)
+        wc = compute_weight(w)
+        need_dx = ctx.needs_input_grad[0]
+        if impl is ref:
+            dx, dw, db = ref.linear_bias_act_bwd(x, wc, y, dy, ctx.relu, need_dx)
+        else:
+            dx, dw, db = impl.linear_bias_act_bwd(x, wc, y, dy, ctx.relu, need_dx,
+                                                  dw_out=_gout(w), db_out=_gout(b))
+        gb = _sink(b, db)
+        gw = _sink(w, dw)
+        return dx, gw, gb, None
+
+
+def linear_bias_act(x, w, b, relu=True):
+    return _LinearFn.apply(x, w, b, relu)
+
+
+# --------------------------------------------------------------------------- conv
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, groups, relu):
+        impl = _impl(x)
+        wc = compute_weight(w)
+        y = impl.conv2d_bias_act(x, wc, b, stride, pad, groups, relu)
+        ctx.save_for_backward(x, y)
+        ctx.w, ctx.b = w, b
+        ctx.cfg = (stride, pad, groups, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        w, b = ctx.w, ctx.b
+        stride, pad, groups, relu = ctx.cfg
+        impl = _impl(x)
+        wc = compute_weight(w)
+        need_dx = ctx.needs_input_grad[0]
+        if impl is ref:
+            dx, dw, db = ref.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx)
+        else:
+            dx, dw, db = impl.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx,
+                                                  dw_out=_gout(w), db_out=_gout(b))
+        gb = _sink(b, db)
+        gw = _sink(w, dw)
+        return dx, gw, gb, None, None, None, None
+
+
+def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True):
+    return _ConvFn.apply(x, w, b, stride, pad, groups, relu)
+
+
+class _ConvG2Fn(torch.autograd.Function):
+    """AlexNet-style 2-group conv with two independent parameter sets
+    (ref ``layers2.py:504-544``).  On CUDA both groups read channel slices of the
+    NHWC input in place (no split/concat copies): the im2col gather takes a channel
+    offset and the GEMM epilogue writes each half of the output with ldc = C_out."""
+
+    @staticmethod
+    def forward(ctx, x, w0, b0, w1, b1, stride, pad, relu):
+        impl = _impl(x)
+        ws = [compute_weight(w0), compute_weight(w1)]
+        if impl is ref:
+            C = x.shape[-1]
+            y0 = ref.conv2d_bias_act(x[..., :C // 2].contiguous(), ws[0], b0, stride, pad, 1, relu)
+            y1 = ref.conv2d_bias_act(x[..., C // 2:].contiguous(), ws[1], b1, stride, pad, 1, relu)
+            y = torch.cat([y0, y1], dim=-1)
+        else:
+            y = impl.conv2d_group2_bias_act(x, ws[0], b0, ws[1], b1, stride, pad, relu)
+        ctx.save_for_backward(x, y)
+        ctx.p = (w0, b0, w1, b1)
+        ctx.cfg = (stride, pad, relu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        w0, b0, w1, b1 = ctx.p
+        stride, pad, relu = ctx.cfg
+        impl = _impl(x)
+        need_dx = ctx.needs_input_grad[0]
+        if impl is ref:
+            C, O = x.shape[-1], y.shape[-1]
+            outs = []
+            for g, (w, b) in enumerate(((w0, b0), (w1, b1))):
+                xs = x[..., g * C // 2:(g + 1) * C // 2].contiguous()
+                ys = y[..., g * O // 2:(g + 1) * O // 2].contiguous()
+                dys = dy[..., g * O // 2:(g + 1) * O // 2].contiguous()
+                outs.append(ref.conv2d_bias_act_bwd(xs, compute_weight(w), ys, dys, stride, pad, 1,
+                                                    relu, need_dx))
+            dx = torch.cat([outs[0][0], outs[1][0]], dim=-1) if need_dx else None
+            grads = (outs[0][1], outs[0][2], outs[1][1], outs[1][2])
+        else:
+            dx, grads = impl.conv2d_group2_bias_act_bwd(
+                x, compute_weight(w0), compute_weight(w1), y, dy, stride, pad, relu, need_dx,
+                outs=(_gout(w0), _gout(b0), _gout(w1), _gout(b1)))
+        gb1 = _sink(b1, grads[3])
+        gw1 = _sink(w1, grads[2])
+        gb0 = _sink(b0, grads[1])
+        gw0 = _sink(w0, grads[0])
+        return dx, gw0, gb0, gw1, gb1, None, None, None
+
+
+def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride=1, pad=0, relu=True):
+    return _ConvG2Fn.apply(x, w0, b0, w1, b1, stride, pad, relu)
+
+
+# --------------------------------------------------------------------------- pool
+class _PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ksize, stride, pad, mode):
+        y = _impl(x).pool2d(x, ksize, stride, pad, mode)
+        ctx.save_for_backward(x, y)
+        ctx.cfg = (ksize, stride, pad, mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y = ctx.saved_tensors
+        dx = _impl(x).pool2d_bwd(x, y, dy.contiguous(), *ctx.cfg)
+        return dx, None, None, None, None
+
+
+def pool2d(x, ksize, stride, pad=0, mode="max"):
+    return _PoolFn.apply(x, ksize, stride, pad, mode)
+
+
+# --------------------------------------------------------------------------- LRN
+class _LRNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, n, k, alpha, beta):
+        impl = _impl(x)
+        y, _ = impl.lrn(x, n, k, alpha, beta)
+        ctx.save_for_backward(x)
+        ctx.cfg = (n, k, alpha, beta)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = _impl(x).lrn_bwd(x, dy.contiguous(), *ctx.cfg)
+        return dx, None, None, None, None
+
+
+def lrn(x, n=5, k=2.0, alpha=1e-4, beta=0.75):
+    return _LRNFn.apply(x, n, k, alpha, beta)
+
+
+# --------------------------------------------------------------------------- dropout
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p_drop, layer_id):
+        if x.is_cuda:
+            from . import cuda_impl
+            y, mask = cuda_impl.dropout_fwd(x, p_drop, layer_id)
+        else:
+            st = rng_state()
+            mask = ref.dropout_mask(x.shape, p_drop, st["seed"] + layer_id, st["step"], x.device)
+            y = ref.dropout(x, p_drop, mask)
+        ctx.save_for_backward(mask)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (mask,) = ctx.saved_tensors
+        if dy.is_cuda:
+            from . import cuda_impl
+            return cuda_impl.dropout_bwd(dy.contiguous(), mask), None, None
+        return dy * mask.to(dy.dtype), None, None
+
+
+_RNG = {"seed": 0x5EED, "step": 0}
+
+
+def rng_state():
+    return _RNG
+
+
+def seed_dropout(seed: int):
+    _RNG["seed"] = int(seed)
+    _RNG["step"] = 0
+
+
+def advance_rng_step():
+    """CPU path only; on CUDA the device step counter advances inside the
+    (graph-captured) step so replays draw fresh masks."""
+    _RNG["step"] += 1
+
+
+def dropout(x, p_drop, training, layer_id=0):
+    """Reference semantics (``layers2.py:885-891``): train → ``mask*x``;
+    eval → ``(1-p)*x`` (no inverted scaling)."""
+    if not training:
+        return x * (1.0 - p_drop)
+    if p_drop <= 0.0:
+        return x
+    return _DropoutFn.apply(x, p_drop, layer_id)
+
+
+# --------------------------------------------------------------------------- softmax + NLL
+class _SoftmaxXentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, err1, err5, dlogits = _impl(logits).softmax_xent(logits, labels)
+        ctx.save_for_backward(dlogits)
+        ctx.in_dtype = logits.dtype
+        ctx.mark_non_differentiable(err1, err5)
+        return loss, err1, err5
+
+    @staticmethod
+    def backward(ctx, gl, g1, g5):
+        (dlogits,) = ctx.saved_tensors
+        # gl is a 0-dim tensor on the same device: no host sync, graph-capturable
+        return (dlogits * gl.to(dlogits.dtype)).to(ctx.in_dtype), None
+
+
+def softmax_xent(logits, labels):
+    """Returns (mean NLL, top-1 error, top-5 error) — fused on CUDA."""
+    return _SoftmaxXentFn.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------- data aug
+def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype=None):
+    if x.is_cuda:
+        from . import cuda_impl
+        return cuda_impl.crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips,
+                                               out_dtype or torch.bfloat16)
+    return ref.crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips,
+                                     out_dtype or torch.float32)

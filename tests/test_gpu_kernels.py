@@ -1,0 +1,238 @@
+"""Numerics of every hand-written sm_100a kernel against a plain-PyTorch fp32 reference
+of the same op (run with ``pytest -m gpu`` on a B200)."""
+import numpy as np
+import pytest
+import torch
+
+from theanompi_b200 import ops
+from theanompi_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _impl():
+    from theanompi_b200.ops import cuda_impl
+    return cuda_impl
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+# ------------------------------------------------------------------ GEMM (tcgen05 / TMEM / TMA)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 384, 512), (200, 136, 328), (128, 4096, 1024), (1000, 72, 136)])
+def test_gemm_majors(M, N, K, a_mn, b_mn):
+    ci = _impl()
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    B = torch.randn(N, K, device=DEV).to(torch.bfloat16)
+    want = A.float() @ B.float().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    lda = M if a_mn else K
+    ldb = N if b_mn else K
+    out = ci.gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, lda=lda, ldb=ldb)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 2e-3, (rel_err(out, want))
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128])
+def test_gemm_epilogue_bias_relu_bf16(bn):
+    ci = _impl()
+    torch.manual_seed(1)
+    M, N, K = 384, 256, 192
+    A = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    B = torch.randn(N, K, device=DEV).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    want = torch.relu(A.float() @ B.float().t() + bias)
+    out = ci.gemm(A, B, M, N, K, bias=bias, bias_mode=1, relu=True, lda=K, ldb=K, bn=bn)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.bfloat16
+    assert rel_err(out, want) < 1e-2
+
+
+def test_gemm_splitk_and_strided_out():
+    ci = _impl()
+    torch.manual_seed(2)
+    M, N, K = 96, 363, 8192          # conv1-wgrad-like: tiny output, long K
+    A = torch.randn(K, M, device=DEV).to(torch.bfloat16)      # MN-major storage [K, M]
+    B = torch.randn(K, 368, device=DEV).to(torch.bfloat16)    # MN-major storage [K, N] with pitch 368
+    want = A.float().t() @ B.float()[:, :N]
+    out = torch.full((M, N), 7.0, device=DEV)
+    ci.gemm(A, B, M, N, K, a_mn=True, b_mn=True, out=out, lda=M, ldb=368, ldc=N)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 2e-3
+
+
+# ------------------------------------------------------------------ layer kernels
+def test_linear_fwd_bwd():
+    torch.manual_seed(3)
+    x = torch.randn(128, 512, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(256, 512, device=DEV) * 0.05).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(256, device=DEV).requires_grad_(True)
+    y = ops.linear_bias_act(x, w, b, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = ref.linear_bias_act(xr, wr, br, True)
+    yr.backward((dy.float() * 1.0))
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(x.grad, xr.grad) < 2e-2
+    assert rel_err(w.grad, wr.grad) < 2e-2
+    assert rel_err(b.grad, br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=4, H=31, W=31, C=3, O=32, k=11, s=4, p=0),      # conv1-like (C=3, K % 8 != 0)
+    dict(N=3, H=13, W=13, C=64, O=96, k=3, s=1, p=1),
+    dict(N=2, H=14, W=14, C=32, O=48, k=5, s=1, p=2),
+    dict(N=2, H=12, W=12, C=64, O=32, k=1, s=1, p=0),      # 1x1 fast path
+])
+def test_conv_fwd_bwd(cfg):
+    torch.manual_seed(4)
+    N, H, W, C, O, k, s, p = (cfg[q] for q in "N H W C O k s p".split())
+    first = C == 3
+    x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16)
+    if not first:
+        x.requires_grad_(True)
+    w = (torch.randn(O, k, k, C, device=DEV) * 0.1).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(O, device=DEV).requires_grad_(True)
+    y = ops.conv2d_bias_act(x, w, b, s, p, 1, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(not first)
+    wr, br = w.detach().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = ref.conv2d_bias_act(xr, wr, br, s, p, 1, True)
+    # reference backward with the SAME mask (bf16 rounding can flip y>0 at exactly 0)
+    dxr, dwr, dbr = ref.conv2d_bias_act_bwd(xr.detach(), wr.detach(), y.detach().float(), dy.float(), s, p, 1, True, not first)
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(w.grad, dwr) < 2e-2
+    assert rel_err(b.grad, dbr) < 2e-2
+    if not first:
+        assert rel_err(x.grad, dxr) < 2e-2
+
+
+def test_conv_group2():
+    torch.manual_seed(5)
+    N, H, W, C, O = 2, 13, 13, 32, 64
+    x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    ws = [(torch.randn(O // 2, 3, 3, C // 2, device=DEV) * 0.1).to(torch.bfloat16).requires_grad_(True) for _ in range(2)]
+    bs = [torch.randn(O // 2, device=DEV).requires_grad_(True) for _ in range(2)]
+    y = ops.conv2d_group2_bias_act(x, ws[0], bs[0], ws[1], bs[1], 1, 1, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    wfull = torch.cat([w.detach().float() for w in ws], 0)
+    bfull = torch.cat([b.detach() for b in bs], 0)
+    yr = ref.conv2d_bias_act(x.detach().float(), wfull, bfull, 1, 1, 2, True)
+    dxr, dwr, dbr = ref.conv2d_bias_act_bwd(x.detach().float(), wfull, y.detach().float(), dy.float(), 1, 1, 2, True, True)
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(x.grad, dxr) < 2e-2
+    assert rel_err(torch.cat([w.grad for w in ws], 0), dwr) < 2e-2
+    assert rel_err(torch.cat([b.grad for b in bs], 0), dbr) < 2e-2
+
+
+@pytest.mark.parametrize("mode,k,s,p", [("max", 3, 2, 0), ("max", 2, 2, 0), ("max", 3, 1, 1), ("avg", 5, 3, 0), ("avg", 7, 1, 0)])
+def test_pool(mode, k, s, p):
+    torch.manual_seed(6)
+    x = torch.randn(2, 15, 15, 16, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    y = ops.pool2d(x, k, s, p, mode)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = ref.pool2d(xr, k, s, p, mode)
+    yr.backward(dy.float())
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(x.grad, xr.grad) < 2e-2
+
+
+def test_lrn():
+    torch.manual_seed(7)
+    x = (torch.randn(2, 9, 9, 96, device=DEV) * 20).to(torch.bfloat16).requires_grad_(True)
+    y = ops.lrn(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    yr, _ = ref.lrn(x.detach().float())
+    dxr = ref.lrn_bwd(x.detach().float(), dy.float())
+    assert rel_err(y, yr) < 1e-2
+    assert rel_err(x.grad, dxr) < 2e-2
+
+
+def test_dropout_mask_statistics_and_bwd():
+    x = torch.ones(128, 4096, device=DEV, dtype=torch.bfloat16, requires_grad=True)
+    y = ops.dropout(x, 0.5, True, layer_id=3)
+    keep = float(y.float().mean())
+    assert abs(keep - 0.5) < 0.01
+    y.backward(torch.ones_like(y))
+    assert torch.equal(x.grad, y.detach())
+    from theanompi_b200.ops import cuda_impl
+    cuda_impl.advance_step(x.device)
+    y2 = ops.dropout(x, 0.5, True, layer_id=3)
+    assert not torch.equal(y2, y)                      # new step → new mask
+    assert float((ops.dropout(x, 0.5, False) .float().mean())) == pytest.approx(0.5, abs=1e-3)
+
+
+def test_softmax_xent():
+    torch.manual_seed(8)
+    lg = (torch.randn(128, 1000, device=DEV) * 3).to(torch.bfloat16).requires_grad_(True)
+    lab = torch.randint(0, 1000, (128,), device=DEV)
+    loss, e1, e5 = ops.softmax_xent(lg, lab)
+    loss.backward()
+    lr, e1r, e5r, dlr = ref.softmax_xent(lg.detach().float(), lab)
+    assert abs(float(loss) - float(lr)) < 1e-3
+    assert abs(float(e1) - float(e1r)) < 1e-6
+    assert abs(float(e5) - float(e5r)) < 1e-6
+    assert rel_err(lg.grad, dlr) < 2e-2
+
+
+def test_crop_mirror_normalize():
+    torch.manual_seed(9)
+    x = torch.randint(0, 256, (4, 32, 32, 3), device=DEV, dtype=torch.uint8)
+    mean = torch.rand(32, 32, 3, device=DEV) * 255
+    offs = torch.tensor([[0, 0], [3, 4], [5, 1], [2, 2]], dtype=torch.int32, device=DEV)
+    flips = torch.tensor([0, 1, 1, 0], dtype=torch.uint8, device=DEV)
+    out = ops.crop_mirror_normalize(x, mean, 1 / 255.0, (27, 27), offs, flips)
+    want = ref.crop_mirror_normalize(x.cpu(), mean.cpu(), 1 / 255.0, (27, 27), offs.cpu(), flips.cpu())
+    assert rel_err(out.cpu(), want) < 1e-2
+
+
+def test_sgd_flat_matches_reference():
+    from theanompi_b200.parallel.arena import FlatArena
+    torch.manual_seed(10)
+    ps = [torch.randn(300, 70), torch.randn(300), torch.randn(5000, 3), torch.randn(17)]
+    wt = ["W", "b", "W", "b"]
+    arena = FlatArena([p.clone() for p in ps], wt, DEV, weight_decay=5e-4)
+    cpu = FlatArena([p.clone() for p in ps], wt, "cpu", weight_decay=5e-4)
+    g = torch.randn(arena.numel)
+    arena.G.copy_(g); cpu.G.copy_(g)
+    from theanompi_b200.utils.opt import FlatSGD
+    for a in (arena, cpu):
+        a.hyper[0] = 0.01
+        s = FlatSGD(a, 0.9, False, True)
+        s.step(0.01, 1)
+        s.step(0.01, 1)
+    torch.cuda.synchronize()
+    assert rel_err(arena.W.cpu(), cpu.W) < 1e-5
+    assert rel_err(arena.U.cpu(), cpu.U) < 1e-5
+    assert rel_err(arena.H.float().cpu(), cpu.W) < 1e-2
+
+
+def test_legacy_kernels_k1_k5():
+    L = ops.native.require()
+    st = torch.cuda.current_stream().cuda_stream
+    x = torch.randn(10000, device=DEV)
+    h = torch.empty(10000, device=DEV, dtype=torch.float16)
+    L.cast_flat(x.data_ptr(), h.data_ptr(), x.numel(), 0, st)
+    back = torch.empty_like(x)
+    L.cast_flat(h.data_ptr(), back.data_ptr(), x.numel(), 1, st)
+    assert rel_err(back, x.half().float()) == 0
+    src = torch.randn(4 * 2500, device=DEV)
+    dst = torch.empty(2500, device=DEV)
+    L.sum_chunks(src.data_ptr(), dst.data_ptr(), 2500, 4, 0, st)
+    assert rel_err(dst, src.view(4, 2500).sum(0)) < 1e-6
+    a, b = torch.randn(999, device=DEV), torch.randn(999, device=DEV)
+    want = a + b
+    L.vecadd(a.data_ptr(), b.data_ptr(), 999, 0, st)
+    assert rel_err(a, want) < 1e-6

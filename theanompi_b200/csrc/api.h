@@ -1,0 +1,80 @@
+// Host-visible API of the sm_100a extension (implemented in the .cu / .cpp files of this directory).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace tmpi {
+
+constexpr int kMaxRanks = 8;
+constexpr int kMaxCommBlocks = 1024;     // signal-pad rows
+
+struct CommCtx {
+  void* arena[kMaxRanks];                // base of rank p's arena as mapped in THIS process
+  uint32_t* sig[kMaxRanks];              // signal pad of rank p: uint32 [kMaxCommBlocks][kMaxRanks]
+  uint32_t* epoch;                       // local: per-block barrier epoch counters [kMaxCommBlocks]
+  void* mc_arena;                        // multicast mapping of the arena (NVLS) or nullptr
+  int rank, world;
+};
+
+struct FusedArgs {
+  CommCtx ctx;
+  long long w_off, g_off, u_off, h_off, wire_off;   // byte offsets of the regions inside the arena (h_off < 0: no shadow)
+  const uint8_t* block_group;
+  GroupTable tab;
+  const float* lr_ptr;                               // device scalar (CUDA-graph friendly)
+  float mu;
+  int nesterov;
+  float inv_k;
+  long long lo, hi;                                  // element range, multiples of kArenaBlock
+  int wire16;                                        // gradients travel as bf16 (cast into the wire region first)
+};
+
+struct ReduceArgs {
+  CommCtx ctx;
+  long long src_off, dst_off, h_off;     // h_off >= 0: also refresh the bf16 shadow from the result (weight averaging)
+  const uint8_t* block_group;
+  GroupTable tab;
+  float scale;
+  long long lo, hi;
+  int skip_local_groups;                 // leave non-exchanged blocks untouched
+};
+
+// ---- gemm_tcgen05.cu
+void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
+               long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
+               cudaStream_t st);
+
+// ---- nn_kernels.cu
+void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
+void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
+void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st);
+void pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st);
+void dropout_fwd(const void* x, void* y, void* mask, long long n, float p_drop, unsigned long long seed, int layer, const void* step, cudaStream_t st);
+void dropout_bwd(const void* dy, const void* mask, void* dx, long long n, cudaStream_t st);
+void advance_step(void* step, cudaStream_t st);
+void softmax_xent(const void* logits, const void* labels, void* dlogits, void* rowstat, void* out3, int B, int C, float weight, cudaStream_t st);
+void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st);
+void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+            long long ldcol, cudaStream_t st);
+void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+            long long ldcol, cudaStream_t st);
+void pad_rows(const void* src, void* dst, long long rows, int cols, long long src_ld, long long dst_ld, cudaStream_t st);
+void transpose_bf16(const void* src, void* dst, int R, int C, cudaStream_t st);
+void crop_mirror_norm(const void* x, int in_kind, const void* mean, int mean_mode, float scale, void* out, int out_bf16, const void* offs,
+                      const void* flips, int N, int H, int W, int C, int ch, int cw, int Cout, cudaStream_t st);
+
+// ---- comm_kernels.cu
+void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, float mu,
+              int nesterov, float inv_k, long long lo, long long hi, int filter, cudaStream_t st);
+void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStream_t st);
+void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t st);
+void device_barrier(const CommCtx& c, cudaStream_t st);
+void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, cudaStream_t st);
+void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, cudaStream_t st);
+void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, long long n, int max_blocks, cudaStream_t st);
+void cast_flat(const void* src, void* dst, long long n, int kind, cudaStream_t st);
+void sum_chunks(const void* src, void* dst, long long chunk, int nchunks, int is_half, cudaStream_t st);
+void vecadd(void* cur, const void* tmp, long long n, int is_half, cudaStream_t st);
+
+}  // namespace tmpi

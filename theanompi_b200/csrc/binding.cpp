@@ -1,0 +1,141 @@
+// pybind11 bindings of the sm_100a extension.  Torch-free on purpose: tensors cross the boundary as raw device
+// pointers (tensor.data_ptr()) and streams as cudaStream_t handles (torch.cuda.current_stream().cuda_stream); the
+// Python wrappers in theanompi_b200/ops/cuda_impl.py and parallel/symmetric.py own shape / dtype / contiguity checks.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "api.h"
+#include "peer_arena.h"
+
+namespace py = pybind11;
+using namespace tmpi;
+typedef uintptr_t ptr_t;
+
+static inline void* P(ptr_t p) { return reinterpret_cast<void*>(p); }
+static inline cudaStream_t S(ptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static GroupTable make_table(const std::vector<float>& lr_mult, const std::vector<float>& wd, const std::vector<int>& exch) {
+  GroupTable t;
+  for (int i = 0; i < kMaxGroups; ++i) {
+    t.lr_mult[i] = i < (int)lr_mult.size() ? lr_mult[i] : 1.f;
+    t.wd[i] = i < (int)wd.size() ? wd[i] : 0.f;
+    t.exch[i] = i < (int)exch.size() ? exch[i] : 1;
+  }
+  return t;
+}
+
+struct PyComm {   // shared_ptr-held wrapper so kernels always see a live mapping
+  std::unique_ptr<PeerArena> pa;
+};
+
+PYBIND11_MODULE(_tmpi_native, m) {
+  m.doc() = "theanompi_b200 native sm_100a kernels and peer-memory runtime";
+  m.def("launch_count", [] { return (unsigned long long)g_launch_count.load(); });
+  m.def("reset_launch_count", [] { g_launch_count.store(0); });
+  m.attr("ARENA_BLOCK") = kArenaBlock;
+  m.attr("MAX_RANKS") = kMaxRanks;
+  m.attr("MAX_COMM_BLOCKS") = kMaxCommBlocks;
+
+  // ---------------------------------------------------------------- GEMM
+  m.def("gemm_bf16", [](ptr_t A, ptr_t B, ptr_t C, ptr_t bias, int M, int N, int K, long long lda, long long ldb, long long ldc,
+                        int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk, ptr_t st) {
+    gemm_bf16(P(A), P(B), P(C), (const float*)P(bias), M, N, K, lda, ldb, ldc, a_mn, b_mn, out_bf16, bias_mode, relu, alpha, bn_hint,
+              splitk, S(st));
+  });
+
+  // ---------------------------------------------------------------- layer kernels
+  m.def("lrn_fwd", [](ptr_t x, ptr_t y, long long rows, int C, int n, float k, float alpha, float beta, ptr_t st) {
+    lrn_fwd(P(x), P(y), rows, C, n, k, alpha, beta, S(st)); });
+  m.def("lrn_bwd", [](ptr_t x, ptr_t dy, ptr_t dx, long long rows, int C, int n, float k, float alpha, float beta, ptr_t st) {
+    lrn_bwd(P(x), P(dy), P(dx), rows, C, n, k, alpha, beta, S(st)); });
+  m.def("pool_fwd", [](ptr_t x, ptr_t y, ptr_t arg, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, ptr_t st) {
+    pool_fwd(P(x), P(y), P(arg), N, H, W, C, Ho, Wo, k, s, p, is_max, S(st)); });
+  m.def("pool_bwd", [](ptr_t dy, ptr_t arg, ptr_t dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, ptr_t st) {
+    pool_bwd(P(dy), P(arg), P(dx), N, H, W, C, Ho, Wo, k, s, p, is_max, S(st)); });
+  m.def("dropout_fwd", [](ptr_t x, ptr_t y, ptr_t mask, long long n, float p, unsigned long long seed, int layer, ptr_t step, ptr_t st) {
+    dropout_fwd(P(x), P(y), P(mask), n, p, seed, layer, P(step), S(st)); });
+  m.def("dropout_bwd", [](ptr_t dy, ptr_t mask, ptr_t dx, long long n, ptr_t st) { dropout_bwd(P(dy), P(mask), P(dx), n, S(st)); });
+  m.def("advance_step", [](ptr_t step, ptr_t st) { advance_step(P(step), S(st)); });
+  m.def("softmax_xent", [](ptr_t logits, ptr_t labels, ptr_t dlogits, ptr_t rowstat, ptr_t out3, int B, int C, float weight, ptr_t st) {
+    softmax_xent(P(logits), P(labels), P(dlogits), P(rowstat), P(out3), B, C, weight, S(st)); });
+  m.def("relu_bias_bwd", [](ptr_t dy, ptr_t y, ptr_t dym, ptr_t db, long long R, int C, long long ld, int relu, ptr_t st) {
+    relu_bias_bwd(P(dy), P(y), P(dym), P(db), R, C, ld, relu, S(st)); });
+  m.def("im2col", [](ptr_t x, ptr_t col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+                     long long ldcol, ptr_t st) { im2col(P(x), P(col), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, S(st)); });
+  m.def("col2im", [](ptr_t dcol, ptr_t dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+                     long long ldcol, ptr_t st) { col2im(P(dcol), P(dx), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, S(st)); });
+  m.def("pad_rows", [](ptr_t src, ptr_t dst, long long rows, int cols, long long src_ld, long long dst_ld, ptr_t st) {
+    pad_rows(P(src), P(dst), rows, cols, src_ld, dst_ld, S(st)); });
+  m.def("transpose_bf16", [](ptr_t src, ptr_t dst, int R, int C, ptr_t st) { transpose_bf16(P(src), P(dst), R, C, S(st)); });
+  m.def("crop_mirror_norm", [](ptr_t x, int in_kind, ptr_t mean, int mean_mode, float scale, ptr_t out, int out_bf16, ptr_t offs, ptr_t flips,
+                               int N, int H, int W, int C, int ch, int cw, int Cout, ptr_t st) {
+    crop_mirror_norm(P(x), in_kind, P(mean), mean_mode, scale, P(out), out_bf16, P(offs), P(flips), N, H, W, C, ch, cw, Cout, S(st)); });
+
+  // ---------------------------------------------------------------- optimizer / legacy kernels
+  m.def("sgd_flat", [](ptr_t W, ptr_t G, ptr_t U, ptr_t H, ptr_t block_group, std::vector<float> lr_mult, std::vector<float> wd,
+                       std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k, long long lo, long long hi, int filter,
+                       ptr_t st) {
+    sgd_flat(P(W), P(G), P(U), P(H), P(block_group), make_table(lr_mult, wd, exch), P(lr_ptr), mu, nesterov, inv_k, lo, hi, filter, S(st)); });
+  m.def("easgd_elastic", [](ptr_t w, ptr_t h, ptr_t center, float alpha, long long n, int max_blocks, ptr_t st) {
+    easgd_elastic(P(w), P(h), P(center), alpha, n, max_blocks, S(st)); });
+  m.def("copy_flat", [](ptr_t dst, ptr_t dst_h, ptr_t src, long long n, int max_blocks, ptr_t st) {
+    copy_flat(P(dst), P(dst_h), P(src), n, max_blocks, S(st)); });
+  m.def("gosgd_merge", [](ptr_t w, ptr_t h, ptr_t b, float a_self, float a_src, long long n, int max_blocks, ptr_t st) {
+    gosgd_merge(P(w), P(h), P(b), a_self, a_src, n, max_blocks, S(st)); });
+  m.def("cast_flat", [](ptr_t src, ptr_t dst, long long n, int kind, ptr_t st) { cast_flat(P(src), P(dst), n, kind, S(st)); });
+  m.def("sum_chunks", [](ptr_t src, ptr_t dst, long long chunk, int nchunks, int is_half, ptr_t st) {
+    sum_chunks(P(src), P(dst), chunk, nchunks, is_half, S(st)); });
+  m.def("vecadd", [](ptr_t cur, ptr_t tmp, long long n, int is_half, ptr_t st) { vecadd(P(cur), P(tmp), n, is_half, S(st)); });
+
+  // ---------------------------------------------------------------- peer memory + fused collectives
+  py::class_<PyComm, std::shared_ptr<PyComm>>(m, "PeerArena")
+      .def(py::init([](int rank, int world, int device, unsigned long long bytes, const std::string& job, bool force_ipc) {
+        auto c = std::make_shared<PyComm>();
+        c->pa.reset(new PeerArena(rank, world, device, (size_t)bytes, job, force_ipc));
+        return c;
+      }), py::arg("rank"), py::arg("world"), py::arg("device"), py::arg("bytes"), py::arg("job"), py::arg("force_ipc") = false)
+      .def("send_handles_to", [](PyComm& c, int peer) { py::gil_scoped_release r; c.pa->send_handles_to(peer); })
+      .def("recv_handles", [](PyComm& c) { py::gil_scoped_release r; c.pa->recv_handles(); })
+      .def("ipc_handles", [](PyComm& c) { return py::bytes(c.pa->ipc_handles()); })
+      .def("ipc_open", [](PyComm& c, int peer, const std::string& h) { c.pa->ipc_open(peer, h); })
+      .def("multicast_supported", [](PyComm& c) { return c.pa->multicast_supported(); })
+      .def("mc_create_and_send", [](PyComm& c) { py::gil_scoped_release r; c.pa->mc_create_and_send(); })
+      .def("mc_recv", [](PyComm& c) { py::gil_scoped_release r; c.pa->mc_recv(); })
+      .def("mc_add_device", [](PyComm& c) { c.pa->mc_add_device(); })
+      .def("mc_bind_and_map", [](PyComm& c) { c.pa->mc_bind_and_map(); })
+      .def("arena_ptr", [](PyComm& c, int p) { return (ptr_t)c.pa->arena_ptr(p); })
+      .def("sig_ptr", [](PyComm& c, int p) { return (ptr_t)c.pa->sig_ptr(p); })
+      .def("mc_ptr", [](PyComm& c) { return (ptr_t)c.pa->mc_ptr(); })
+      .def("arena_bytes", [](PyComm& c) { return (unsigned long long)c.pa->arena_bytes(); })
+      .def("mode", [](PyComm& c) { return c.pa->mode(); })
+      .def("vmm_error", [](PyComm& c) { return c.pa->vmm_error(); })
+      .def("device_barrier", [](PyComm& c, ptr_t st) { device_barrier(c.pa->ctx(), S(st)); })
+      .def("fused_allreduce_sgd",
+           [](PyComm& c, long long w_off, long long g_off, long long u_off, long long h_off, long long wire_off, ptr_t block_group,
+              std::vector<float> lr_mult, std::vector<float> wd, std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k,
+              long long lo, long long hi, int wire16, int algo, int max_blocks, ptr_t st) {
+             FusedArgs a;
+             a.ctx = c.pa->ctx();
+             a.w_off = w_off; a.g_off = g_off; a.u_off = u_off; a.h_off = h_off; a.wire_off = wire_off;
+             a.block_group = (const uint8_t*)P(block_group);
+             a.tab = make_table(lr_mult, wd, exch);
+             a.lr_ptr = (const float*)P(lr_ptr); a.mu = mu; a.nesterov = nesterov; a.inv_k = inv_k; a.lo = lo; a.hi = hi; a.wire16 = wire16;
+             fused_allreduce_sgd(a, algo, max_blocks, S(st));
+           })
+      .def("allreduce_flat",
+           [](PyComm& c, long long src_off, long long dst_off, long long h_off, ptr_t block_group, std::vector<float> lr_mult,
+              std::vector<float> wd, std::vector<int> exch, float scale, long long lo, long long hi, int skip_local, int algo,
+              int max_blocks, ptr_t st) {
+             ReduceArgs a;
+             a.ctx = c.pa->ctx();
+             a.src_off = src_off; a.dst_off = dst_off; a.h_off = h_off;
+             a.block_group = (const uint8_t*)P(block_group);
+             a.tab = make_table(lr_mult, wd, exch);
+             a.scale = scale; a.lo = lo; a.hi = hi; a.skip_local_groups = skip_local;
+             allreduce_flat(a, algo, max_blocks, S(st));
+           });
+}

@@ -1,0 +1,475 @@
+// Flat-arena optimizer + collective kernels (sm_100a, NVLink 5 / NVSwitch peer memory).
+//
+// Every rank maps every peer's *symmetric arena* (W | G | U | R | H regions at identical byte offsets) and a
+// small *signal pad* into its own address space (csrc/peer_arena.cpp).  The kernels below therefore issue
+// plain ld/st (or multimem.* when a multicast mapping exists) on peer pointers — no NCCL/MPI call is on the
+// path.  What the reference does in three separate stages per tensor
+//     Barrier → ncclAllReduce(vels→vels2) → one elementwise update kernel per tensor
+// (theanompi/lib/exchanger.py:120-134, exchanger_strategy.py:121-127, opt.py:181-268) is ONE launch here:
+//     flag barrier → read all peers' gradients → average → weight-decay/momentum/lr update → bf16 shadow
+//     [→ push the updated slice to the peers] → flag barrier.
+//
+//   sgd_flat            k = 1 instance (no peers): fused momentum-SGD over a block range
+//   fused_oneshot_sgd   every rank reduces the whole range itself (latency-optimal, small buckets)
+//   fused_twoshot_sgd   reduce-scatter → update owned slice → push updated weights to all peers (bandwidth-optimal)
+//   fused_nvls_sgd      same with multimem.ld_reduce / multimem.st (reduction + broadcast inside the NVSwitch)
+//   allreduce_*         plain sum/avg into a destination region (classic cdd vels→vels2, 'avg' weight averaging)
+//   easgd_elastic       d = α(w − c); w −= d; c += d   on the center's memory over NVLink   (exchanger.py:188-211)
+//   gosgd_*             push / merge / pull-merge of weights with push-sum weights α     (exchanger.py:450-462)
+//   K1..K5 of the reference (float2half/half2float, sumfloats/sumhalfs, vecadd/vecaddhalf) for the legacy strategies.
+#include "common.cuh"
+#include "api.h"
+
+namespace tmpi {
+
+constexpr int kThreads = 256;            // one float4 per thread per 1024-element arena block
+
+// ------------------------------------------------------------------ memory helpers
+__device__ __forceinline__ float4 ld_sys_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ld_sys_u2(const void* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_f4(float* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_u2(void* p, uint2 v) {
+  asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ float4 mc_ld_reduce_f4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 mc_ld_reduce_bf16x4(const void* mc) {
+  uint2 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v2.bf16x2 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(mc) : "memory");
+  return v;
+}
+__device__ __forceinline__ void mc_st_f4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_st_u2(void* mc, uint2 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(mc), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)) : "memory");
+}
+__device__ __forceinline__ uint2 pack_bf16x4(float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r; r.x = *reinterpret_cast<uint32_t*>(&a); r.y = *reinterpret_cast<uint32_t*>(&b); return r;
+}
+__device__ __forceinline__ float4 unpack_bf16x4(uint2 u) {
+  float2 a = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+template <typename T> __device__ __forceinline__ T* region(const CommCtx& c, int p, long long off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(c.arena[p]) + off);
+}
+
+// ------------------------------------------------------------------ cross-rank per-block flag barrier
+// Block b of every rank increments slot [b][my rank] on every peer (red.release.sys) and spins until its own
+// slots [b][p] reach the block's epoch (ld.acquire.sys).  Epochs live in device memory, so the same captured
+// CUDA graph can be replayed.  Bounded spin: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void block_barrier(const CommCtx& c) {
+  __syncthreads();
+  uint32_t* ep = c.epoch + blockIdx.x;
+  const uint32_t target = *ep + 1u;
+  if ((int)threadIdx.x < c.world) {
+    uint32_t* remote = c.sig[threadIdx.x] + (size_t)blockIdx.x * kMaxRanks + c.rank;
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(remote) : "memory");
+    const uint32_t* mine = c.sig[c.rank] + (size_t)blockIdx.x * kMaxRanks + threadIdx.x;
+    uint32_t v;
+    long long t0 = clock64();
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - target) >= 0) break;
+      if (clock64() - t0 > 60000000000LL) { __trap(); }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *ep = target;
+}
+
+// ------------------------------------------------------------------ the SGD math (one float4)
+struct Hyper { float lr, mu, inv_k; int nesterov; };
+
+__device__ __forceinline__ void sgd4(float4& w, float4& u, const float4& gsum, const Hyper& h, float lrm, float wd) {
+  const float lr = h.lr * lrm;
+#define TMPI_SGD1(W, U, G)                                   \
+  {                                                          \
+    const float ge = G * h.inv_k + wd * W;                   \
+    U = h.mu * U + ge;                                       \
+    W -= lr * (h.nesterov ? (ge + h.mu * U) : U);            \
+  }
+  TMPI_SGD1(w.x, u.x, gsum.x) TMPI_SGD1(w.y, u.y, gsum.y) TMPI_SGD1(w.z, u.z, gsum.z) TMPI_SGD1(w.w, u.w, gsum.w)
+#undef TMPI_SGD1
+}
+
+// ============================================================================ k = 1: local fused SGD
+// filter: 0 all groups, 1 only non-exchanged (BN) groups, 2 only exchanged groups
+__global__ void __launch_bounds__(kThreads) sgd_flat_kernel(float* __restrict__ W, const float* __restrict__ G, float* __restrict__ U,
+                                                            __nv_bfloat16* __restrict__ H, const uint8_t* __restrict__ block_group,
+                                                            GroupTable tab, const float* __restrict__ lr_ptr, float mu, int nesterov,
+                                                            float inv_k, long long blk_lo, long long blk_hi, int filter) {
+  const Hyper h{*lr_ptr, mu, inv_k, nesterov};
+  for (long long b = blk_lo + blockIdx.x; b < blk_hi; b += gridDim.x) {
+    const int g = block_group[b];
+    if ((filter == 1 && tab.exch[g]) || (filter == 2 && !tab.exch[g])) continue;
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 w = *reinterpret_cast<const float4*>(W + i);
+    float4 u = *reinterpret_cast<const float4*>(U + i);
+    const float4 gg = *reinterpret_cast<const float4*>(G + i);
+    sgd4(w, u, gg, h, tab.lr_mult[g], tab.wd[g]);
+    *reinterpret_cast<float4*>(W + i) = w;
+    *reinterpret_cast<float4*>(U + i) = u;
+    if (H) *reinterpret_cast<uint2*>(H + i) = pack_bf16x4(w);
+  }
+}
+
+void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, float mu,
+              int nesterov, float inv_k, long long lo, long long hi, int filter, cudaStream_t st) {
+  if (lo % kArenaBlock || hi % kArenaBlock) throw std::runtime_error("sgd_flat: range must be block aligned");
+  const long long nb = (hi - lo) / kArenaBlock;
+  if (nb <= 0) return;
+  int grid = (int)std::min<long long>(nb, (long long)sm_count() * 8);
+  sgd_flat_kernel<<<grid, kThreads, 0, st>>>((float*)W, (const float*)G, (float*)U, (__nv_bfloat16*)H, (const uint8_t*)block_group, tab,
+                                             (const float*)lr_ptr, mu, nesterov, inv_k, lo / kArenaBlock, hi / kArenaBlock, filter);
+  count_launch(); TMPI_CHECK_LAUNCH("sgd_flat");
+}
+
+// ============================================================================ fused collectives
+__device__ __forceinline__ void local_block_update(const FusedArgs& a, const Hyper& h, long long b, int g) {
+  const long long i = b * kArenaBlock + threadIdx.x * 4;
+  float* W = region<float>(a.ctx, a.ctx.rank, a.w_off);
+  float* U = region<float>(a.ctx, a.ctx.rank, a.u_off);
+  const float* G = region<float>(a.ctx, a.ctx.rank, a.g_off);
+  float4 w = *reinterpret_cast<const float4*>(W + i), u = *reinterpret_cast<const float4*>(U + i);
+  const float4 gg = *reinterpret_cast<const float4*>(G + i);
+  Hyper hl = h; hl.inv_k = 1.f;
+  sgd4(w, u, gg, hl, a.tab.lr_mult[g], a.tab.wd[g]);
+  *reinterpret_cast<float4*>(W + i) = w;
+  *reinterpret_cast<float4*>(U + i) = u;
+  if (a.h_off >= 0) *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.h_off) + i) = pack_bf16x4(w);
+}
+
+// cast the caller's own gradient block to the bf16 wire region
+__device__ __forceinline__ void cast_block_to_wire(const FusedArgs& a, long long b) {
+  const long long i = b * kArenaBlock + threadIdx.x * 4;
+  const float4 gg = *reinterpret_cast<const float4*>(region<float>(a.ctx, a.ctx.rank, a.g_off) + i);
+  *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.wire_off) + i) = pack_bf16x4(gg);
+}
+
+__device__ __forceinline__ float4 gather_grad(const FusedArgs& a, long long i) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.wire16) {
+    uint2 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) v[p] = ld_sys_u2(region<__nv_bfloat16>(a.ctx, p, a.wire_off) + i);
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) acc = add4(acc, unpack_bf16x4(v[p]));
+  } else {
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) v[p] = ld_sys_f4(region<float>(a.ctx, p, a.g_off) + i);
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) acc = add4(acc, v[p]);     // fixed order → bit-identical on all ranks
+  }
+  return acc;
+}
+
+// ---- one-shot: every rank reduces every block itself
+__global__ void __launch_bounds__(kThreads) fused_oneshot_sgd_kernel(const FusedArgs a) {
+  const Hyper h{*a.lr_ptr, a.mu, a.inv_k, a.nesterov};
+  const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
+  if (a.wire16) {
+    for (long long b = blo + blockIdx.x; b < bhi; b += gridDim.x)
+      if (a.tab.exch[a.block_group[b]]) cast_block_to_wire(a, b);
+  }
+  block_barrier(a.ctx);                                  // peers' gradients (or wire copies) are complete
+  float* W = region<float>(a.ctx, a.ctx.rank, a.w_off);
+  float* U = region<float>(a.ctx, a.ctx.rank, a.u_off);
+  for (long long b = blo + blockIdx.x; b < bhi; b += gridDim.x) {
+    const int g = a.block_group[b];
+    if (!a.tab.exch[g]) { local_block_update(a, h, b, g); continue; }
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    const float4 gs = gather_grad(a, i);
+    float4 w = *reinterpret_cast<const float4*>(W + i), u = *reinterpret_cast<const float4*>(U + i);
+    sgd4(w, u, gs, h, a.tab.lr_mult[g], a.tab.wd[g]);
+    *reinterpret_cast<float4*>(W + i) = w;
+    *reinterpret_cast<float4*>(U + i) = u;
+    if (a.h_off >= 0) *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.h_off) + i) = pack_bf16x4(w);
+  }
+  block_barrier(a.ctx);                                  // nobody overwrites G while a peer still reads it
+}
+
+// ---- two-shot: rank r owns a contiguous slice of the range; reduce → update → push W (+H) to every peer
+__global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const FusedArgs a, int use_nvls) {
+  const Hyper h{*a.lr_ptr, a.mu, a.inv_k, a.nesterov};
+  const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
+  const long long nb = bhi - blo;
+  const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
+  const int R = a.ctx.rank, Wn = a.ctx.world;
+  if (a.wire16) {
+    // block b casts, for every owner r, the strip of r's slice that block b of rank r will read
+    for (int r = 0; r < Wn; ++r) {
+      const long long s0 = blo + r * per, s1 = min(bhi, s0 + per);
+      for (long long b = s0 + blockIdx.x; b < s1; b += gridDim.x)
+        if (a.tab.exch[a.block_group[b]]) cast_block_to_wire(a, b);
+    }
+  }
+  block_barrier(a.ctx);
+  const long long s0 = blo + R * per, s1 = min(bhi, s0 + per);
+  float* W = region<float>(a.ctx, R, a.w_off);
+  float* U = region<float>(a.ctx, R, a.u_off);
+  for (long long b = s0 + blockIdx.x; b < s1; b += gridDim.x) {
+    const int g = a.block_group[b];
+    if (!a.tab.exch[g]) continue;
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 gs;
+    if (use_nvls) {
+      gs = a.wire16 ? unpack_bf16x4(mc_ld_reduce_bf16x4(reinterpret_cast<char*>(a.ctx.mc_arena) + a.wire_off + i * 2))
+                    : mc_ld_reduce_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.g_off) + i);
+    } else {
+      gs = gather_grad(a, i);
+    }
+    float4 w = *reinterpret_cast<const float4*>(W + i), u = *reinterpret_cast<const float4*>(U + i);
+    sgd4(w, u, gs, h, a.tab.lr_mult[g], a.tab.wd[g]);
+    *reinterpret_cast<float4*>(U + i) = u;
+    const uint2 wh = pack_bf16x4(w);
+    if (use_nvls) {
+      mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
+      if (a.h_off >= 0) mc_st_u2(reinterpret_cast<char*>(a.ctx.mc_arena) + a.h_off + i * 2, wh);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxRanks; ++p) {
+        if (p < Wn) {
+          st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
+          if (a.h_off >= 0) st_u2(region<__nv_bfloat16>(a.ctx, p, a.h_off) + i, wh);
+        }
+      }
+    }
+  }
+  // non-exchanged (BN) blocks: every rank updates all of them locally
+  for (long long b = blo + blockIdx.x; b < bhi; b += gridDim.x) {
+    const int g = a.block_group[b];
+    if (!a.tab.exch[g]) local_block_update(a, h, b, g);
+  }
+  block_barrier(a.ctx);                                  // pushed weights are visible everywhere
+}
+
+static int pick_grid(long long nblocks, int max_blocks) {
+  long long g = std::min<long long>(nblocks, (long long)max_blocks);
+  if (g < 1) g = 1;
+  if (g > kMaxCommBlocks) g = kMaxCommBlocks;
+  return (int)g;
+}
+
+// algo: 0 one-shot, 1 two-shot (P2P), 2 two-shot NVLS
+void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStream_t st) {
+  if (a.lo % kArenaBlock || a.hi % kArenaBlock) throw std::runtime_error("fused_allreduce_sgd: range must be block aligned");
+  const long long nb = (a.hi - a.lo) / kArenaBlock;
+  if (nb <= 0) return;
+  if (algo == 2 && a.ctx.mc_arena == nullptr) throw std::runtime_error("fused_allreduce_sgd: NVLS requested without a multicast mapping");
+  if (algo == 0) {
+    fused_oneshot_sgd_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
+  } else {
+    const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
+    fused_twoshot_sgd_kernel<<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, algo == 2 ? 1 : 0);
+  }
+  count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd");
+}
+
+// ============================================================================ plain flat allreduce (sum * scale) src region → dst region
+__global__ void __launch_bounds__(kThreads) allreduce_oneshot_kernel(const ReduceArgs a) {
+  const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
+  block_barrier(a.ctx);
+  float* D = region<float>(a.ctx, a.ctx.rank, a.dst_off);
+  for (long long b = blo + blockIdx.x; b < bhi; b += gridDim.x) {
+    if (a.skip_local_groups && !a.tab.exch[a.block_group[b]]) continue;
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 v[kMaxRanks];
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) v[p] = ld_sys_f4(region<float>(a.ctx, p, a.src_off) + i);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) acc = add4(acc, v[p]);
+    acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+    *reinterpret_cast<float4*>(D + i) = acc;
+    if (a.h_off >= 0) *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.h_off) + i) = pack_bf16x4(acc);
+  }
+  block_barrier(a.ctx);
+}
+
+__global__ void __launch_bounds__(kThreads) allreduce_twoshot_kernel(const ReduceArgs a, int use_nvls) {
+  const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
+  const long long per = (bhi - blo + a.ctx.world - 1) / a.ctx.world;
+  const long long s0 = blo + a.ctx.rank * per, s1 = min(bhi, s0 + per);
+  block_barrier(a.ctx);
+  for (long long b = s0 + blockIdx.x; b < s1; b += gridDim.x) {
+    if (a.skip_local_groups && !a.tab.exch[a.block_group[b]]) continue;
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (use_nvls) {
+      acc = mc_ld_reduce_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.src_off) + i);
+    } else {
+      float4 v[kMaxRanks];
+#pragma unroll
+      for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) v[p] = ld_sys_f4(region<float>(a.ctx, p, a.src_off) + i);
+#pragma unroll
+      for (int p = 0; p < kMaxRanks; ++p) if (p < a.ctx.world) acc = add4(acc, v[p]);
+    }
+    acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+    const uint2 hh = pack_bf16x4(acc);
+    if (use_nvls) {
+      mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.dst_off) + i, acc);
+      if (a.h_off >= 0) mc_st_u2(reinterpret_cast<char*>(a.ctx.mc_arena) + a.h_off + i * 2, hh);
+    } else {
+#pragma unroll
+      for (int p = 0; p < kMaxRanks; ++p) {
+        if (p < a.ctx.world) {
+          st_f4(region<float>(a.ctx, p, a.dst_off) + i, acc);
+          if (a.h_off >= 0) st_u2(region<__nv_bfloat16>(a.ctx, p, a.h_off) + i, hh);
+        }
+      }
+    }
+  }
+  block_barrier(a.ctx);
+}
+
+void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t st) {
+  if (a.lo % kArenaBlock || a.hi % kArenaBlock) throw std::runtime_error("allreduce_flat: range must be block aligned");
+  const long long nb = (a.hi - a.lo) / kArenaBlock;
+  if (nb <= 0) return;
+  if (algo == 0 && a.src_off == a.dst_off) throw std::runtime_error("allreduce_flat: one-shot cannot run in place");
+  if (algo == 2 && a.ctx.mc_arena == nullptr) throw std::runtime_error("allreduce_flat: NVLS requested without a multicast mapping");
+  if (algo == 0) allreduce_oneshot_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
+  else allreduce_twoshot_kernel<<<pick_grid((nb + a.ctx.world - 1) / a.ctx.world, max_blocks), kThreads, 0, st>>>(a, algo == 2 ? 1 : 0);
+  count_launch(); TMPI_CHECK_LAUNCH("allreduce_flat");
+}
+
+// standalone device barrier (tests / stream alignment)
+__global__ void barrier_kernel(const CommCtx c) { block_barrier(c); }
+void device_barrier(const CommCtx& c, cudaStream_t st) {
+  barrier_kernel<<<1, 32, 0, st>>>(c);
+  count_launch(); TMPI_CHECK_LAUNCH("device_barrier");
+}
+
+// ============================================================================ EASGD elastic exchange (worker side, center over NVLink)
+__global__ void __launch_bounds__(kThreads) easgd_elastic_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ h, float* c /*peer*/,
+                                                                 float alpha, long long nblk) {
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    float4 cv = ld_sys_f4(c + i);
+    const float4 d = make_float4(alpha * (wv.x - cv.x), alpha * (wv.y - cv.y), alpha * (wv.z - cv.z), alpha * (wv.w - cv.w));
+    wv.x -= d.x; wv.y -= d.y; wv.z -= d.z; wv.w -= d.w;
+    cv.x += d.x; cv.y += d.y; cv.z += d.z; cv.w += d.w;
+    *reinterpret_cast<float4*>(w + i) = wv;
+    st_f4(c + i, cv);
+    if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(wv);
+  }
+  __threadfence_system();
+}
+void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, cudaStream_t st) {
+  if (n % kArenaBlock) throw std::runtime_error("easgd_elastic: n must be block aligned");
+  const long long nb = n / kArenaBlock;
+  if (nb <= 0) return;
+  easgd_elastic_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (float*)center, alpha, nb);
+  count_launch(); TMPI_CHECK_LAUNCH("easgd_elastic");
+}
+
+// dst = src (+ bf16 shadow) over peer memory: EASGD copy_to_local, GOSGD push into the peer's mailbox region
+__global__ void __launch_bounds__(kThreads) copy_flat_kernel(float* dst, __nv_bfloat16* dst_h, const float* src, long long nblk) {
+  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    const float4 v = ld_sys_f4(src + i);
+    st_f4(dst + i, v);
+    if (dst_h) *reinterpret_cast<uint2*>(dst_h + i) = pack_bf16x4(v);
+  }
+  __threadfence_system();
+}
+void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, cudaStream_t st) {
+  if (n % kArenaBlock) throw std::runtime_error("copy_flat: n must be block aligned");
+  const long long nb = n / kArenaBlock;
+  if (nb <= 0) return;
+  copy_flat_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)dst, (__nv_bfloat16*)dst_h, (const float*)src, nb);
+  count_launch(); TMPI_CHECK_LAUNCH("copy_flat");
+}
+
+// ============================================================================ GOSGD merge:  w ← (a_self·w + a_src·b) / (a_self + a_src)
+// `b` may be a local mailbox region or the sender's weights mapped over NVLink (pull-merge, one pass).
+__global__ void __launch_bounds__(kThreads) gosgd_merge_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ h, const float* b,
+                                                               float a_self, float a_src, long long nblk) {
+  const float inv = 1.f / (a_self + a_src);
+  const float ca = a_self * inv, cb = a_src * inv;
+  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const long long i = blk * kArenaBlock + threadIdx.x * 4;
+    float4 wv = *reinterpret_cast<const float4*>(w + i);
+    const float4 bv = ld_sys_f4(b + i);
+    wv.x = ca * wv.x + cb * bv.x; wv.y = ca * wv.y + cb * bv.y; wv.z = ca * wv.z + cb * bv.z; wv.w = ca * wv.w + cb * bv.w;
+    *reinterpret_cast<float4*>(w + i) = wv;
+    if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(wv);
+  }
+}
+void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, long long n, int max_blocks, cudaStream_t st) {
+  if (n % kArenaBlock) throw std::runtime_error("gosgd_merge: n must be block aligned");
+  const long long nb = n / kArenaBlock;
+  if (nb <= 0) return;
+  gosgd_merge_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (const float*)b, a_self, a_src, nb);
+  count_launch(); TMPI_CHECK_LAUNCH("gosgd_merge");
+}
+
+// ============================================================================ reference kernels K1..K5 (legacy strategies)
+template <typename TI, typename TO> __global__ void cast_kernel(const TI* __restrict__ s, TO* __restrict__ d, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) d[i] = (TO)(float)s[i];
+}
+// kind: 0 f32→f16, 1 f16→f32, 2 f32→bf16, 3 bf16→f32     (K1/K5: float2half / half2float)
+void cast_flat(const void* src, void* dst, long long n, int kind, cudaStream_t st) {
+  const int g = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  if (n <= 0) return;
+  switch (kind) {
+    case 0: cast_kernel<float, __half><<<g, 256, 0, st>>>((const float*)src, (__half*)dst, n); break;
+    case 1: cast_kernel<__half, float><<<g, 256, 0, st>>>((const __half*)src, (float*)dst, n); break;
+    case 2: cast_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n); break;
+    case 3: cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n); break;
+    default: throw std::runtime_error("cast_flat: bad kind");
+  }
+  count_launch(); TMPI_CHECK_LAUNCH("cast_flat");
+}
+
+// K2/K3 sumfloats / sumhalfs with the reference's loop bug fixed: dst[i] = Σ_j src[i + chunk*j], fp32 accumulate
+template <typename T> __global__ void sum_chunks_kernel(const T* __restrict__ s, T* __restrict__ d, long long chunk, int nchunks) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chunk; i += (long long)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < nchunks; ++j) acc += (float)s[i + chunk * j];
+    d[i] = (T)acc;
+  }
+}
+void sum_chunks(const void* src, void* dst, long long chunk, int nchunks, int is_half, cudaStream_t st) {
+  if (chunk <= 0) return;
+  const int g = (int)std::min<long long>((chunk + 255) / 256, (long long)sm_count() * 16);
+  if (is_half) sum_chunks_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, (__half*)dst, chunk, nchunks);
+  else sum_chunks_kernel<float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, chunk, nchunks);
+  count_launch(); TMPI_CHECK_LAUNCH("sum_chunks");
+}
+
+// K4/K5 vecadd / vecaddhalf: cur[i] += tmp[i]
+template <typename T> __global__ void vecadd_kernel(T* __restrict__ cur, const T* __restrict__ tmp, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    cur[i] = (T)((float)cur[i] + (float)tmp[i]);
+}
+void vecadd(void* cur, const void* tmp, long long n, int is_half, cudaStream_t st) {
+  if (n <= 0) return;
+  const int g = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
+  if (is_half) vecadd_kernel<__half><<<g, 256, 0, st>>>((__half*)cur, (const __half*)tmp, n);
+  else vecadd_kernel<float><<<g, 256, 0, st>>>((float*)cur, (const float*)tmp, n);
+  count_launch(); TMPI_CHECK_LAUNCH("vecadd");
+}
+
+}  // namespace tmpi

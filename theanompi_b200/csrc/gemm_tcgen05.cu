@@ -1,0 +1,394 @@
+// Hand-written Blackwell GEMM:  C[M,N] = alpha * op(A) · op(B)  (+bias, +ReLU)  bf16 in, fp32 accumulate.
+//
+//   * operands staged global→shared by TMA (cp.async.bulk.tensor.2d, 128B swizzle),
+//   * tcgen05.mma.cta_group::1.kind::f16 issued by ONE thread, accumulator in TMEM,
+//   * mbarrier producer/consumer ring between the TMA warp and the MMA warp,
+//   * tcgen05.commit hands smem slots back / signals the epilogue,
+//   * 4 epilogue warps read TMEM with tcgen05.ld (32x32b.x32) and fuse bias / ReLU /
+//     bf16 cast / split-K reduction into the store.
+//
+// Both operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous):
+// forward, dgrad and wgrad of FC and (im2col) conv layers all run on this one kernel without any
+// transposed copies (reference: cuBLAS SGEMM through Theano, layers2.py:927-929, GpuCorrMM :597-653).
+//
+// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = epilogue
+// (warp_id % 4 selects the TMEM lane quarter a warp may read).
+#include "common.cuh"
+#include "api.h"
+#include <cuda.h>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+namespace tmpi {
+std::atomic<unsigned long long> g_launch_count{0};
+
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+
+template <int BN> struct Cfg {
+  static constexpr int STAGES = (BN == 128) ? 5 : (BN == 64 ? 6 : 8);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = (BN < 32) ? 32 : BN;   // power of two >= 32
+};
+
+struct Params {
+  void* C;
+  const float* bias;
+  float alpha;
+  int M, N, K;
+  long long ldc;
+  int a_mn, b_mn;       // 1 = operand is MN-major in global memory
+  int out_bf16;         // 1 = bf16 output, 0 = fp32
+  int bias_mode;        // 0 none, 1 per-column (N), 2 per-row (M)
+  int relu;
+  int kb_per_split;     // k-blocks per grid.z slice
+  int atomic_out;       // 1 = fp32 atomicAdd (split-K)
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) { __trap(); }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address      bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // leading byte off   bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride byte off    bits [32,46)
+  d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                 // layout type: SWIZZLE_128B
+  return d;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024B alignment
+  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, C::TMEM_COLS); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        if (!p.a_mn) {
+          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
+            tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
+            tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // K-major, SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the 128 B row.
+      // MN-major, SW128: 64-element MN atoms BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+      //                  advance 16 k-rows = 2048 B per UMMA_K.
+      const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_sbo = 1024u, a_step = p.a_mn ? 128u : 2u;
+      const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_sbo = 1024u, b_step = p.b_mn ? 128u : 2u;
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+        const uint32_t sb = sa + C::A_BYTES;
+        const uint64_t adesc0 = make_smem_desc(sa, a_lbo, a_sbo);
+        const uint64_t bdesc0 = make_smem_desc(sb, b_lbo, b_sbo);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));             // frees the smem slot once these MMAs retire
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tmem_full_bar);                  // accumulator complete → epilogue
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM → registers → global =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + 32 * q + lane;
+    const bool m_ok = m < p.M;
+    float bias_m = 0.f;
+    if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
+      tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+      tmem_ld_wait();
+      const int nb = n0 + 32 * c;
+      if (!m_ok || nb >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]) * p.alpha;
+        if (p.bias_mode == 1) { x += (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f; }
+        else if (p.bias_mode == 2) { x += bias_m; }
+        if (p.relu) x = fmaxf(x, 0.f);
+        v[j] = x;
+      }
+      const bool full = (nb + 32 <= p.N);
+      if (p.atomic_out) {
+        float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (full || nb + j < p.N) atomicAdd(dst + j, v[j]);
+      } else if (p.out_bf16) {
+        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f_to_bf16(v[j]);
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_acc, C::TMEM_COLS); }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q);
+    if (e == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (PFN_encodeTiled)f;
+    (void)cudaGetLastError();
+  });
+  if (!fn) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  return fn;
+}
+
+// 2-D bf16 tensor map: dims {inner, outer}, row pitch in bytes, box {64, box_outer}, 128B swizzle, zero OOB fill.
+static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand base must be 16B aligned");
+  if ((pitch_bytes & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand row pitch must be a multiple of 16 bytes");
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{ptr, inner, outer, pitch_bytes, box_outer};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {64u, box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+
+template <int BN>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int splits, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
+    attr_set = true;
+  }
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits);
+  gemm_bf16_tcgen05<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  count_launch();
+  TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05");
+}
+
+}  // namespace gemm
+
+// C[M,N] (ldc) = alpha * op(A) op(B) + bias, optional ReLU.
+//   a_mn == 0: A is [M, K] with row pitch lda (elements);  a_mn == 1: A is [K, M] with row pitch lda.
+//   b_mn == 0: B is [N, K] with row pitch ldb;             b_mn == 1: B is [K, N] with row pitch ldb.
+//   bn_hint: 0 = auto, else 32/64/128.  splitk: 0 = auto, 1 = none, >1 = forced (fp32 output only, no bias/relu).
+void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
+               long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
+               cudaStream_t st) {
+  using namespace gemm;
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  const int sms = sm_count();
+  const int mt = (M + BM - 1) / BM;
+  int BN = bn_hint;
+  if (BN == 0) {
+    BN = 128;
+    if (mt * ((N + 127) / 128) < sms && N >= 64) BN = 64;
+    if (BN == 64 && mt * ((N + 63) / 64) < sms && !b_mn && N >= 32) BN = 32;
+  }
+  if (b_mn && BN < 64) BN = 64;
+  const int nt = (N + BN - 1) / BN;
+  const int num_kb = (K + BK - 1) / BK;
+  const bool can_split = (!out_bf16) && bias_mode == 0 && !relu;
+  int splits = 1;
+  if (splitk > 1 && can_split) splits = splitk;
+  else if (splitk == 0 && can_split && mt * nt < sms && num_kb >= 8) {
+    splits = (sms + mt * nt - 1) / (mt * nt);
+    if (splits > num_kb / 4) splits = num_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;          // every slice owns >= 1 k-block
+
+  Params p;
+  p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
+  p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
+  if (splits > 1) {
+    // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
+    check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");
+  }
+  CUtensorMap ta = a_mn ? make_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64u)
+                        : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, (uint32_t)BM);
+  CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64u)
+                        : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN);
+  if (BN == 128) launch<128>(ta, tb, p, splits, st);
+  else if (BN == 64) launch<64>(ta, tb, p, splits, st);
+  else launch<32>(ta, tb, p, splits, st);
+}
+
+}  // namespace tmpi

@@ -1,0 +1,650 @@
+// Fused non-GEMM layer kernels for sm_100a: LRN fwd/bwd, max/avg pooling fwd/bwd, dropout (Philox),
+// softmax + NLL + top-1/top-5 error (+ dlogits), ReLU-mask + bias-gradient reduction, NHWC im2col /
+// col2im-gather for the implicit-GEMM convolutions, normalise+crop+mirror for the loader.
+// All activations are NHWC bf16 with C % 8 == 0 (16-byte vectors) unless noted; math is fp32.
+// Reference ops: theanompi/models/layers2.py (LRN :753-809, Pool :402-428, Dropout :864-908,
+// Softmax :937-997, Crop/Subtract :223-347) and data/utils.py:42-129 (crop_and_mirror).
+#include "common.cuh"
+#include "api.h"
+
+namespace tmpi {
+
+static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// ============================================================================ LRN
+template <int HALF>
+__global__ void lrn_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int C,
+                               float k, float alpha, float beta) {
+  const int nvec = C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nvec) return;
+  const long long r = idx / nvec;
+  const int cv = (int)(idx % nvec);
+  const __nv_bfloat16* row = x + r * C;
+  float xs[24];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const int c = (cv - 1 + v) * 8;
+    if (c >= 0 && c < C) unpack8(*reinterpret_cast<const bf16x8*>(row + c), xs + 8 * v);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xs[8 * v + i] = 0.f;
+    }
+  }
+  float out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = -HALF; j <= HALF; ++j) { float t = xs[8 + i + j]; s += t * t; }
+    const float scale = k + alpha * s;
+    out[i] = xs[8 + i] * exp2f(-beta * __log2f(scale));
+  }
+  *reinterpret_cast<bf16x8*>(y + r * C + cv * 8) = pack8(out);
+}
+
+template <int HALF>
+__global__ void lrn_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                               __nv_bfloat16* __restrict__ dx, long long rows, int C, float k, float alpha, float beta) {
+  const int nvec = C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * nvec) return;
+  const long long r = idx / nvec;
+  const int cv = (int)(idx % nvec);
+  float xs[24], ds[24];
+#pragma unroll
+  for (int v = 0; v < 3; ++v) {
+    const int c = (cv - 1 + v) * 8;
+    if (c >= 0 && c < C) {
+      unpack8(*reinterpret_cast<const bf16x8*>(x + r * C + c), xs + 8 * v);
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + r * C + c), ds + 8 * v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { xs[8 * v + i] = 0.f; ds[8 * v + i] = 0.f; }
+    }
+  }
+  // t_i = dy_i * x_i * s_i^(-beta-1) for i in [8-HALF, 16+HALF); p_i = s_i^-beta for the centre 8
+  float t[8 + 2 * HALF];
+  float pc[8];
+#pragma unroll
+  for (int a = 0; a < 8 + 2 * HALF; ++a) {
+    const int L = 8 - HALF + a;
+    float s = 0.f;
+#pragma unroll
+    for (int j = -HALF; j <= HALF; ++j) { float q = xs[L + j]; s += q * q; }
+    const float scale = k + alpha * s;
+    const float p = exp2f(-beta * __log2f(scale));
+    t[a] = ds[L] * xs[L] * p / scale;
+    if (a >= HALF && a < HALF + 8) pc[a - HALF] = p;
+  }
+  float out[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j <= 2 * HALF; ++j) acc += t[i + j];
+    out[i] = ds[8 + i] * pc[i] - 2.f * alpha * beta * xs[8 + i] * acc;
+  }
+  *reinterpret_cast<bf16x8*>(dx + r * C + cv * 8) = pack8(out);
+}
+
+void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("lrn: C must be a multiple of 8");
+  const int half = n / 2;
+  long long total = rows * (C / 8);
+  const int B = 256;
+  auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
+  switch (half) {
+    case 1: lrn_fwd_kernel<1><<<grid_for(total, B), B, 0, st>>>(X, Y, rows, C, k, alpha, beta); break;
+    case 2: lrn_fwd_kernel<2><<<grid_for(total, B), B, 0, st>>>(X, Y, rows, C, k, alpha, beta); break;
+    case 3: lrn_fwd_kernel<3><<<grid_for(total, B), B, 0, st>>>(X, Y, rows, C, k, alpha, beta); break;
+    case 4: lrn_fwd_kernel<4><<<grid_for(total, B), B, 0, st>>>(X, Y, rows, C, k, alpha, beta); break;
+    default: throw std::runtime_error("lrn: window n must be 3,5,7 or 9");
+  }
+  count_launch(); TMPI_CHECK_LAUNCH("lrn_fwd");
+}
+
+void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("lrn: C must be a multiple of 8");
+  const int half = n / 2;
+  long long total = rows * (C / 8);
+  const int B = 256;
+  auto X = (const __nv_bfloat16*)x; auto DY = (const __nv_bfloat16*)dy; auto DX = (__nv_bfloat16*)dx;
+  switch (half) {
+    case 1: lrn_bwd_kernel<1><<<grid_for(total, B), B, 0, st>>>(X, DY, DX, rows, C, k, alpha, beta); break;
+    case 2: lrn_bwd_kernel<2><<<grid_for(total, B), B, 0, st>>>(X, DY, DX, rows, C, k, alpha, beta); break;
+    case 3: lrn_bwd_kernel<3><<<grid_for(total, B), B, 0, st>>>(X, DY, DX, rows, C, k, alpha, beta); break;
+    case 4: lrn_bwd_kernel<4><<<grid_for(total, B), B, 0, st>>>(X, DY, DX, rows, C, k, alpha, beta); break;
+    default: throw std::runtime_error("lrn: window n must be 3,5,7 or 9");
+  }
+  count_launch(); TMPI_CHECK_LAUNCH("lrn_bwd");
+}
+
+// ============================================================================ pooling
+struct PoolGeom { int N, H, W, C, Ho, Wo, k, s, p; };
+
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ arg, PoolGeom g) {
+  const int nvec = g.C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.N * g.Ho * g.Wo * nvec;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int wo = (int)(t % g.Wo); t /= g.Wo;
+  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+  float best[8]; int bi[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+  for (int kh = 0; kh < g.k; ++kh) {
+    const int h = ho * g.s - g.p + kh;
+    if (h < 0 || h >= g.H) continue;
+    for (int kw = 0; kw < g.k; ++kw) {
+      const int w = wo * g.s - g.p + kw;
+      if (w < 0 || w >= g.W) continue;
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * g.H + h) * g.W + w) * g.C + cv * 8), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * g.k + kw; }
+    }
+  }
+  const long long o = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8;
+  *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
+  uint2 packed;
+  packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+  packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+  *reinterpret_cast<uint2*>(arg + o) = packed;
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
+                                   __nv_bfloat16* __restrict__ dx, PoolGeom g) {
+  const int nvec = g.C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.N * g.H * g.W * nvec;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int w = (int)(t % g.W); t /= g.W;
+  const int h = (int)(t % g.H); const int n = (int)(t / g.H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  // outputs whose window covers (h, w): ho*s - p <= h < ho*s - p + k
+  int ho_lo = (h + g.p - g.k + g.s) / g.s; if (h + g.p - g.k + 1 <= 0) ho_lo = 0;
+  int wo_lo = (w + g.p - g.k + g.s) / g.s; if (w + g.p - g.k + 1 <= 0) wo_lo = 0;
+  const int ho_hi = min(g.Ho - 1, (h + g.p) / g.s);
+  const int wo_hi = min(g.Wo - 1, (w + g.p) / g.s);
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    const int kh = h + g.p - ho * g.s;
+    if (kh < 0 || kh >= g.k) continue;
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      const int kw = w + g.p - wo * g.s;
+      if (kw < 0 || kw >= g.k) continue;
+      const long long o = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8;
+      const uint2 a = *reinterpret_cast<const uint2*>(arg + o);
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + o), d);
+      const uint32_t me = (uint32_t)(kh * g.k + kw);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ai = ((i < 4 ? a.x : a.y) >> (8 * (i & 3))) & 0xFFu;
+        if (ai == me) acc[i] += d[i];
+      }
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dx + (((long long)n * g.H + h) * g.W + w) * g.C + cv * 8) = pack8(acc);
+}
+
+__device__ __forceinline__ int avg_count(const PoolGeom& g, int ho, int wo) {
+  const int h0 = max(0, ho * g.s - g.p), h1 = min(g.H, ho * g.s - g.p + g.k);
+  const int w0 = max(0, wo * g.s - g.p), w1 = min(g.W, wo * g.s - g.p + g.k);
+  return max(1, (h1 - h0) * (w1 - w0));
+}
+
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, PoolGeom g) {
+  const int nvec = g.C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.N * g.Ho * g.Wo * nvec;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int wo = (int)(t % g.Wo); t /= g.Wo;
+  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int kh = 0; kh < g.k; ++kh) {
+    const int h = ho * g.s - g.p + kh;
+    if (h < 0 || h >= g.H) continue;
+    for (int kw = 0; kw < g.k; ++kw) {
+      const int w = wo * g.s - g.p + kw;
+      if (w < 0 || w >= g.W) continue;
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * g.H + h) * g.W + w) * g.C + cv * 8), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  const float inv = 1.f / (float)avg_count(g, ho, wo);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  *reinterpret_cast<bf16x8*>(y + (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8) = pack8(acc);
+}
+
+__global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, PoolGeom g) {
+  const int nvec = g.C >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.N * g.H * g.W * nvec;
+  if (idx >= total) return;
+  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int w = (int)(t % g.W); t /= g.W;
+  const int h = (int)(t % g.H); const int n = (int)(t / g.H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int ho_hi = min(g.Ho - 1, (h + g.p) / g.s);
+  const int wo_hi = min(g.Wo - 1, (w + g.p) / g.s);
+  for (int ho = 0; ho <= ho_hi; ++ho) {
+    const int kh = h + g.p - ho * g.s;
+    if (kh < 0 || kh >= g.k) continue;
+    for (int wo = 0; wo <= wo_hi; ++wo) {
+      const int kw = w + g.p - wo * g.s;
+      if (kw < 0 || kw >= g.k) continue;
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8), d);
+      const float inv = 1.f / (float)avg_count(g, ho, wo);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += d[i] * inv;
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dx + (((long long)n * g.H + h) * g.W + w) * g.C + cv * 8) = pack8(acc);
+}
+
+void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("pool: C must be a multiple of 8");
+  PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
+  long long total = (long long)N * Ho * Wo * (C / 8);
+  if (is_max) maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)arg, g);
+  else avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
+  count_launch(); TMPI_CHECK_LAUNCH("pool_fwd");
+}
+
+void pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st) {
+  PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
+  long long total = (long long)N * H * W * (C / 8);
+  if (is_max) maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)arg, (__nv_bfloat16*)dx, g);
+  else avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, g);
+  count_launch(); TMPI_CHECK_LAUNCH("pool_bwd");
+}
+
+// ============================================================================ dropout (Philox4x32-10)
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// y = x * keep; keep drawn with P(keep) = 1 - p_drop from Philox keyed by (seed, layer) and counter (idx, *step)
+__global__ void dropout_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ mask,
+                                   long long n8, float p_drop, unsigned long long seed, uint32_t layer,
+                                   const unsigned long long* __restrict__ step) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  const unsigned long long stp = *step;
+  uint32_t r[4];
+  philox4x32((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)stp, (uint32_t)(stp >> 32), (uint32_t)seed,
+             (uint32_t)(seed >> 32) ^ (layer * 0x9E3779B9u), r);
+  const uint32_t thr = (uint32_t)(p_drop * 65536.f);
+  float v[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(x + idx * 8), v);
+  uint32_t mlo = 0, mhi = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t u = (r[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+    const uint32_t keep = u >= thr ? 1u : 0u;
+    v[i] = keep ? v[i] : 0.f;
+    if (i < 4) mlo |= keep << (8 * i); else mhi |= keep << (8 * (i - 4));
+  }
+  *reinterpret_cast<bf16x8*>(y + idx * 8) = pack8(v);
+  *reinterpret_cast<uint2*>(mask + idx * 8) = make_uint2(mlo, mhi);
+}
+
+__global__ void dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ mask,
+                                   __nv_bfloat16* __restrict__ dx, long long n8) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n8) return;
+  float v[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(dy + idx * 8), v);
+  const uint2 m = *reinterpret_cast<const uint2*>(mask + idx * 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const uint32_t k = ((i < 4 ? m.x : m.y) >> (8 * (i & 3))) & 0xFFu; if (!k) v[i] = 0.f; }
+  *reinterpret_cast<bf16x8*>(dx + idx * 8) = pack8(v);
+}
+
+__global__ void advance_step_kernel(unsigned long long* step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1ull; }
+
+void dropout_fwd(const void* x, void* y, void* mask, long long n, float p_drop, unsigned long long seed, int layer, const void* step, cudaStream_t st) {
+  if (n % 8) throw std::runtime_error("dropout: numel must be a multiple of 8");
+  dropout_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)mask, n / 8, p_drop, seed,
+                                                           (uint32_t)layer, (const unsigned long long*)step);
+  count_launch(); TMPI_CHECK_LAUNCH("dropout_fwd");
+}
+void dropout_bwd(const void* dy, const void* mask, void* dx, long long n, cudaStream_t st) {
+  dropout_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)mask, (__nv_bfloat16*)dx, n / 8);
+  count_launch(); TMPI_CHECK_LAUNCH("dropout_bwd");
+}
+void advance_step(void* step, cudaStream_t st) {
+  advance_step_kernel<<<1, 32, 0, st>>>((unsigned long long*)step);
+  count_launch(); TMPI_CHECK_LAUNCH("advance_step");
+}
+
+// ============================================================================ softmax + NLL + errors + dlogits
+// one CTA per row; rowstat[b] = {nll, err1, err5}; dlogits = (softmax - onehot) * scale
+__global__ void softmax_xent_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ labels,
+                                    __nv_bfloat16* __restrict__ dlogits, float* __restrict__ rowstat, int C, float scale) {
+  const int b = blockIdx.x;
+  const __nv_bfloat16* row = logits + (long long)b * C;
+  const int label = (int)labels[b];
+  __shared__ float red[32];
+  __shared__ float bcast;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, bf16_to_f(row[c]));
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (warp == 0) { float v = lane < nw ? red[lane] : -INFINITY; v = warp_max(v); if (lane == 0) bcast = v; }
+  __syncthreads();
+  mx = bcast;
+  __syncthreads();
+  const float lab = bf16_to_f(row[label]);
+  float se = 0.f, gt = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float v = bf16_to_f(row[c]);
+    se += __expf(v - mx);
+    gt += (v > lab || (v == lab && c < label)) ? 1.f : 0.f;     // rank of the label's logit
+  }
+  se = warp_sum(se); gt = warp_sum(gt);
+  if (lane == 0) { red[warp] = se; }
+  __syncthreads();
+  if (warp == 0) { float v = lane < nw ? red[lane] : 0.f; v = warp_sum(v); if (lane == 0) bcast = v; }
+  __syncthreads();
+  se = bcast;
+  __syncthreads();
+  if (lane == 0) { red[warp] = gt; }
+  __syncthreads();
+  if (warp == 0) { float v = lane < nw ? red[lane] : 0.f; v = warp_sum(v); if (lane == 0) bcast = v; }
+  __syncthreads();
+  gt = bcast;
+  const float inv = 1.f / se;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float pr = __expf(bf16_to_f(row[c]) - mx) * inv;
+    if (c == label) pr -= 1.f;
+    dlogits[(long long)b * C + c] = f_to_bf16(pr * scale);
+  }
+  if (threadIdx.x == 0) {
+    rowstat[3 * b + 0] = -(lab - mx - __logf(se));
+    rowstat[3 * b + 1] = gt >= 1.f ? 1.f : 0.f;
+    rowstat[3 * b + 2] = gt >= 5.f ? 1.f : 0.f;
+  }
+}
+
+__global__ void rowstat_mean_kernel(const float* __restrict__ rowstat, float* __restrict__ out, int B, float weight) {
+  __shared__ float red[3][32];
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) { a += rowstat[3 * i]; b += rowstat[3 * i + 1]; c += rowstat[3 * i + 2]; }
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { red[0][warp] = a; red[1][warp] = b; red[2][warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    a = lane < nw ? red[0][lane] : 0.f; b = lane < nw ? red[1][lane] : 0.f; c = lane < nw ? red[2][lane] : 0.f;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { out[0] = weight * a / B; out[1] = b / B; out[2] = c / B; }
+  }
+}
+
+void softmax_xent(const void* logits, const void* labels, void* dlogits, void* rowstat, void* out3, int B, int C, float weight, cudaStream_t st) {
+  softmax_xent_kernel<<<B, 256, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)labels, (__nv_bfloat16*)dlogits, (float*)rowstat, C, weight / (float)B);
+  count_launch(); TMPI_CHECK_LAUNCH("softmax_xent");
+  rowstat_mean_kernel<<<1, 256, 0, st>>>((const float*)rowstat, (float*)out3, B, weight);
+  count_launch(); TMPI_CHECK_LAUNCH("rowstat_mean");
+}
+
+// ============================================================================ ReLU mask + bias gradient
+// dym = dy * (y > 0) (bf16, contiguous [R, C]);  db[c] += sum_r dym[r, c]   (db pre-zeroed by the launcher)
+// dy / y have row pitch ld (elements) so channel slices of a wider tensor work (grouped conv).
+template <bool RELU, bool WRITE>
+__global__ void relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ dym, float* __restrict__ db, long long R, int C,
+                                     long long ld, int VT, int rows_per_cta) {
+  extern __shared__ float sm[];                       // [RL][VT*8]
+  const int nvec = C >> 3;
+  const int RL = blockDim.x / VT;
+  const int tv = threadIdx.x % VT, tr = threadIdx.x / VT;
+  const int cv = blockIdx.y * VT + tv;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (tr < RL && cv < nvec) {
+    for (long long r = r0 + tr; r < min(R, r0 + rows_per_cta); r += RL) {
+      float d[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dy + r * ld + cv * 8), d);
+      if (RELU) {
+        float v[8];
+        unpack8(*reinterpret_cast<const bf16x8*>(y + r * ld + cv * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) d[i] = 0.f;
+      }
+      if (WRITE) *reinterpret_cast<bf16x8*>(dym + r * C + cv * 8) = pack8(d);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += d[i];
+    }
+  }
+  if (db == nullptr) return;
+  if (tr < RL) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[(tr * VT + tv) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < VT * 8) {
+    const int v = threadIdx.x / 8, i = threadIdx.x % 8;
+    const int c = (blockIdx.y * VT + v) * 8 + i;
+    if (c < C) {
+      float s = 0.f;
+      for (int t = 0; t < RL; ++t) s += sm[(t * VT + v) * 8 + i];
+      atomicAdd(db + c, s);
+    }
+  }
+}
+
+void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("relu_bias_bwd: C must be a multiple of 8");
+  const int nvec = C / 8;
+  const int VT = nvec < 32 ? nvec : 32;
+  const int RL = 256 / VT;
+  const int rows_per_cta = RL * 16;
+  dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
+  const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
+  if (db) check_cuda(cudaMemsetAsync(db, 0, (size_t)C * 4, st), "relu_bias_bwd memset");
+  const bool write = dym != nullptr;
+  auto DY = (const __nv_bfloat16*)dy; auto Y = (const __nv_bfloat16*)y; auto DM = (__nv_bfloat16*)dym; auto DB = (float*)db;
+  if (relu && write) relu_bias_bwd_kernel<true, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
+  else if (relu) relu_bias_bwd_kernel<true, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
+  else if (write) relu_bias_bwd_kernel<false, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
+  else relu_bias_bwd_kernel<false, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
+  count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd");
+}
+
+// ============================================================================ im2col / col2im (NHWC, bf16)
+struct ConvGeom { int N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p; long long ldcol; int K; };
+
+// col[m, (kh*KW+kw)*Cg + c] = x[n, ho*s-p+kh, wo*s-p+kw, c_off+c]   (zero outside the image)
+__global__ void im2col_vec8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
+  const int cvn = g.Cg >> 3;
+  const int per_m = g.KH * g.KW * cvn;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)g.N * g.Ho * g.Wo;
+  if (idx >= M * per_m) return;
+  const long long m = idx / per_m; int rem = (int)(idx % per_m);
+  const int kk = rem / cvn, cv = rem % cvn;
+  const int kh = kk / g.KW, kw = kk % g.KW;
+  const int wo = (int)(m % g.Wo); long long t = m / g.Wo;
+  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+  const int h = ho * g.s - g.p + kh, w = wo * g.s - g.p + kw;
+  bf16x8 v;
+  if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+    v = *reinterpret_cast<const bf16x8*>(x + (((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off + cv * 8);
+  else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  }
+  *reinterpret_cast<bf16x8*>(col + m * g.ldcol + (long long)kk * g.Cg + cv * 8) = v;
+}
+
+// generic (any Cg): one thread per (m, kh*KW+kw); the extra index KH*KW zero-fills the K..ldcol padding
+__global__ void im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
+  const int per_m = g.KH * g.KW + 1;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long M = (long long)g.N * g.Ho * g.Wo;
+  if (idx >= M * per_m) return;
+  const long long m = idx / per_m; const int kk = (int)(idx % per_m);
+  __nv_bfloat16* dst = col + m * g.ldcol;
+  if (kk == g.KH * g.KW) { for (int c = g.K; c < g.ldcol; ++c) dst[c] = f_to_bf16(0.f); return; }
+  const int kh = kk / g.KW, kw = kk % g.KW;
+  const int wo = (int)(m % g.Wo); long long t = m / g.Wo;
+  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+  const int h = ho * g.s - g.p + kh, w = wo * g.s - g.p + kw;
+  const bool ok = (h >= 0 && h < g.H && w >= 0 && w < g.W);
+  const __nv_bfloat16* src = x + (((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off;
+  dst += (long long)kk * g.Cg;
+  for (int c = 0; c < g.Cg; ++c) dst[c] = ok ? src[c] : f_to_bf16(0.f);
+}
+
+// dx[n,h,w,c_off+c] = sum over (kh,kw) with (h+p-kh)%s==0, (w+p-kw)%s==0 of dcol[m(n,ho,wo), (kh*KW+kw)*Cg + c]
+__global__ void col2im_vec8_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, ConvGeom g) {
+  const int cvn = g.Cg >> 3;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)g.N * g.H * g.W * cvn;
+  if (idx >= total) return;
+  const int cv = (int)(idx % cvn); long long t = idx / cvn;
+  const int w = (int)(t % g.W); t /= g.W;
+  const int h = (int)(t % g.H); const int n = (int)(t / g.H);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int kh = 0; kh < g.KH; ++kh) {
+    const int th = h + g.p - kh;
+    if (th < 0 || th % g.s) continue;
+    const int ho = th / g.s;
+    if (ho >= g.Ho) continue;
+    for (int kw = 0; kw < g.KW; ++kw) {
+      const int tw = w + g.p - kw;
+      if (tw < 0 || tw % g.s) continue;
+      const int wo = tw / g.s;
+      if (wo >= g.Wo) continue;
+      const long long m = ((long long)n * g.Ho + ho) * g.Wo + wo;
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(dcol + m * g.ldcol + (long long)(kh * g.KW + kw) * g.Cg + cv * 8), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dx + (((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off + cv * 8) = pack8(acc);
+}
+
+void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+            long long ldcol, cudaStream_t st) {
+  ConvGeom g{N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, KH * KW * Cg};
+  long long M = (long long)N * Ho * Wo;
+  if (Cg % 8 == 0 && c_off % 8 == 0 && Ctot % 8 == 0 && ldcol % 8 == 0) {
+    long long total = M * KH * KW * (Cg / 8);
+    im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
+  } else {
+    long long total = M * (KH * KW + 1);
+    im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
+  }
+  count_launch(); TMPI_CHECK_LAUNCH("im2col");
+}
+
+void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
+            long long ldcol, cudaStream_t st) {
+  if (Cg % 8 || c_off % 8 || Ctot % 8 || ldcol % 8) throw std::runtime_error("col2im: channel counts must be multiples of 8");
+  ConvGeom g{N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, KH * KW * Cg};
+  long long total = (long long)N * H * W * (Cg / 8);
+  col2im_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, g);
+  count_launch(); TMPI_CHECK_LAUNCH("col2im");
+}
+
+// ============================================================================ small utility kernels
+// rows x cols (pitch src_ld) → rows x dst_ld with zero padding (K-padding of conv1 weights for TMA pitch rules)
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long rows, int cols,
+                                long long src_ld, long long dst_ld) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * dst_ld) return;
+  const long long r = idx / dst_ld; const int c = (int)(idx % dst_ld);
+  dst[idx] = c < cols ? src[r * src_ld + c] : f_to_bf16(0.f);
+}
+void pad_rows(const void* src, void* dst, long long rows, int cols, long long src_ld, long long dst_ld, cudaStream_t st) {
+  pad_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols, src_ld, dst_ld);
+  count_launch(); TMPI_CHECK_LAUNCH("pad_rows");
+}
+
+__global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
+  __shared__ __nv_bfloat16 tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r = blockIdx.y * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8) if (c < C && r + j < R) tile[threadIdx.y + j][threadIdx.x] = src[(long long)(r + j) * C + c];
+  __syncthreads();
+  int oc = blockIdx.y * 32 + threadIdx.x, orow = blockIdx.x * 32 + threadIdx.y;
+  for (int j = 0; j < 32; j += 8) if (oc < R && orow + j < C) dst[(long long)(orow + j) * R + oc] = tile[threadIdx.x][threadIdx.y + j];
+}
+void transpose_bf16(const void* src, void* dst, int R, int C, cudaStream_t st) {
+  dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, C);
+  count_launch(); TMPI_CHECK_LAUNCH("transpose_bf16");
+}
+
+// ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32
+template <typename Tin, typename Tout>
+__global__ void crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode, float scale,
+                                        Tout* __restrict__ out, const int* __restrict__ offs, const uint8_t* __restrict__ flips,
+                                        int N, int H, int W, int C, int ch, int cw, int Cout) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)N * ch * cw;
+  if (idx >= total) return;
+  const int ox = (int)(idx % cw); long long t = idx / cw;
+  const int oy = (int)(t % ch); const int n = (int)(t / ch);
+  const int y0 = offs[2 * n], x0 = offs[2 * n + 1];
+  const int sy = y0 + oy;
+  const int sx = x0 + (flips[n] ? (cw - 1 - ox) : ox);
+  const long long sp = (((long long)n * H + sy) * W + sx) * C;
+  const long long mp = mean_mode == 2 ? ((long long)sy * W + sx) * C : 0;
+  Tout* o = out + idx * Cout;
+  for (int c = 0; c < Cout; ++c) {
+    float v = 0.f;
+    if (c < C) {
+      const float m = mean_mode == 0 ? mean[0] : (mean_mode == 1 ? mean[c] : mean[mp + c]);
+      v = ((float)x[sp + c] - m) * scale;
+    }
+    o[c] = (Tout)v;
+  }
+}
+
+void crop_mirror_norm(const void* x, int in_kind /*0 u8, 1 bf16, 2 f32*/, const void* mean, int mean_mode, float scale, void* out,
+                      int out_bf16, const void* offs, const void* flips, int N, int H, int W, int C, int ch, int cw, int Cout, cudaStream_t st) {
+  long long total = (long long)N * ch * cw;
+  const int g = grid_for(total, 256);
+  auto M = (const float*)mean; auto O = (const int*)offs; auto F = (const uint8_t*)flips;
+#define CMN(TI, TO) crop_mirror_norm_kernel<TI, TO><<<g, 256, 0, st>>>((const TI*)x, M, mean_mode, scale, (TO*)out, O, F, N, H, W, C, ch, cw, Cout)
+  if (in_kind == 0) { if (out_bf16) CMN(uint8_t, __nv_bfloat16); else CMN(uint8_t, float); }
+  else if (in_kind == 1) { if (out_bf16) CMN(__nv_bfloat16, __nv_bfloat16); else CMN(__nv_bfloat16, float); }
+  else { if (out_bf16) CMN(float, __nv_bfloat16); else CMN(float, float); }
+#undef CMN
+  count_launch(); TMPI_CHECK_LAUNCH("crop_mirror_norm");
+}
+
+}  // namespace tmpi

@@ -108,7 +108,7 @@ class ModelBase(object):
         count_params(self.params, verbose=False)
         allocator = self.config.get("arena_allocator")
         self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta,
-                               with_recv=False, allocator=allocator)
+                               with_recv=allocator is not None, allocator=allocator)
         self.shared_lr = SharedScalar(self.arena.hyper, 0, self.base_lr)
         self.sgd = FlatSGD(self.arena, self.mu, self.use_nesterov_momentum, self.use_momentum)
         B = self.batch_size
@@ -220,7 +220,7 @@ class ModelBase(object):
     def compile_train(self, *args):
         self.compiled_train_fn_list.extend(args)
 
-    def compile_iter_fns(self, sync_type="avg", aggregate="momentum"):
+    def compile_iter_fns(self, sync_type="avg", aggregate="momentum", fused_tail=None):
         """``sync_type='cdd'``: split step (get_vel / exchange / descent_vel);
         ``'avg'``: self-contained local update (k = 1), the exchanger then averages
         weights.  Fixes SURVEY §2.9 #5/#7: every model accepts ``sync_type`` and 'avg'
@@ -228,9 +228,9 @@ class ModelBase(object):
         start = time.time()
         self.sync_type = sync_type
         k = self.size if sync_type == "cdd" else 1
-        if k > 1:
+        if k > 1 and fused_tail is None:
             _ = self.arena.R                      # allocate the receive region
-        pre_model_iter_fn(self, k, aggregate=aggregate)
+        pre_model_iter_fn(self, k, aggregate=aggregate, fused_tail=fused_tail)
         if self.verbose:
             print("Compile time: %.3f s" % (time.time() - start))
 

@@ -1,0 +1,375 @@
+"""CUDA implementations of the functional ops: thin, checked wrappers that hand raw
+device pointers of torch tensors to the hand-written sm_100a kernels in ``csrc/``.
+
+GEMM-shaped work (FC forward/dgrad/wgrad; conv forward/dgrad/wgrad through an NHWC
+im2col gather) runs on ONE kernel, ``gemm_bf16`` (TMA → smem → ``tcgen05.mma`` →
+TMEM → fused epilogue, see ``csrc/gemm_tcgen05.cu``).  Operand-major flags make
+transposed copies unnecessary:
+
+    forward   y  = x · Wᵀ        A = x   (K-major)   B = W   (K-major)   + bias + ReLU → bf16
+    dgrad     dx = dy · W        A = dy  (K-major)   B = W   (MN-major)               → bf16
+    wgrad     dW = dyᵀ · x       A = dy  (MN-major)  B = x   (MN-major)  split-K      → fp32 (straight into the arena's G)
+
+Everything raises if the extension is missing — there is no eager fallback on a GPU.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import native
+
+_STEP = {}          # device index -> int64[1] step counter used by the dropout Philox stream
+BF16 = torch.bfloat16
+
+
+def L():
+    return native.require()
+
+
+def _st(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def step_counter(device):
+    idx = torch.device(device).index
+    if idx is None:
+        idx = torch.cuda.current_device()
+    if idx not in _STEP:
+        _STEP[idx] = torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", idx))
+    return _STEP[idx]
+
+
+def advance_step(device):
+    s = step_counter(device)
+    L().advance_step(s.data_ptr(), _st(s))
+
+
+def _bf(t):
+    return t if t.dtype == BF16 else t.to(BF16)
+
+
+def _rows8(t2d):
+    """Return a 2-D bf16 tensor whose row pitch is a multiple of 8 elements (TMA: 16 B) —
+    the tensor itself when it already is, else a zero-padded copy (rare, tiny shapes)."""
+    assert t2d.dim() == 2
+    if t2d.stride(1) == 1 and t2d.stride(0) % 8 == 0 and t2d.data_ptr() % 16 == 0:
+        return t2d, t2d.stride(0)
+    R, C = t2d.shape
+    ld = (C + 7) // 8 * 8
+    out = torch.zeros((R, ld), dtype=BF16, device=t2d.device)
+    out[:, :C] = t2d
+    return out, ld
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm(a, b, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, bias_mode=0,
+         relu=False, alpha=1.0, lda=None, ldb=None, ldc=None, bn=0, splitk=0):
+    """``out[M,N] = alpha * op(a) @ op(b) (+bias)(ReLU)``; ``a``/``b`` are bf16 tensors whose
+    storage is described by (major flag, leading dimension)."""
+    dev = a.device
+    if out is None:
+        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+    if ldc is None:
+        ldc = out.stride(0) if out.dim() == 2 else N
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    L().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), _p(bias), int(M), int(N), int(K), int(lda), int(ldb),
+                  int(ldc), int(bool(a_mn)), int(bool(b_mn)), int(out.dtype == BF16), int(bias_mode), int(bool(relu)),
+                  float(alpha), int(bn), int(splitk), _st(a))
+    return out
+
+
+# --------------------------------------------------------------------------- linear
+def linear_bias_act(x, w, b, relu=True):
+    x2 = _bf(x).contiguous()
+    B_, I = x2.shape
+    O = w.shape[0]
+    xa, lda = _rows8(x2)
+    wa, ldb = _rows8(_bf(w))
+    return gemm(xa, wa, B_, O, I, bias=b.float() if b is not None and b.dtype != torch.float32 else b,
+                bias_mode=1 if b is not None else 0, relu=relu, lda=lda, ldb=ldb)
+
+
+def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld):
+    """dym = dy ⊙ (y > 0) (contiguous [R, C]) and db = Σ_rows dym in one pass."""
+    dev = dy.device
+    db = db_out if db_out is not None else torch.empty(C, dtype=torch.float32, device=dev)
+    contiguous = (ld == C)
+    if relu or not contiguous:
+        dym = torch.empty((R, C), dtype=BF16, device=dev)
+        L().relu_bias_bwd(dy.data_ptr(), _p(y), dym.data_ptr(), db.data_ptr(), int(R), int(C), int(ld), int(bool(relu)), _st(dy))
+    else:
+        dym = dy
+        L().relu_bias_bwd(dy.data_ptr(), 0, 0, db.data_ptr(), int(R), int(C), int(ld), 0, _st(dy))
+    return dym, db
+
+
+def linear_bias_act_bwd(x, w, y, dy, relu, need_dx, dw_out=None, db_out=None):
+    x2 = _bf(x).contiguous()
+    dy = _bf(dy).contiguous()
+    B_, I = x2.shape
+    O = w.shape[0]
+    if O % 8 or I % 8:
+        return _linear_bwd_padded(x2, w, y, dy, relu, need_dx, dw_out, db_out)
+    dym, db = _mask_and_bias_grad(dy, y, relu, db_out.view(-1) if db_out is not None else None, B_, O, O)
+    wb = _bf(w)
+    dx = None
+    if need_dx:
+        dx = gemm(dym, wb, B_, I, O, a_mn=False, b_mn=True, lda=O, ldb=I)
+    dw = dw_out if dw_out is not None else torch.empty((O, I), dtype=torch.float32, device=x.device)
+    gemm(dym, x2, O, I, B_, a_mn=True, b_mn=True, out=dw, lda=O, ldb=I, ldc=I)
+    return dx, dw, db
+
+
+def _linear_bwd_padded(x2, w, y, dy, relu, need_dx, dw_out, db_out):
+    """Shapes whose pitches violate the 16-byte TMA rule (e.g. a 10-class test head): pad to 8."""
+    B_, I = x2.shape
+    O = w.shape[0]
+    Op, Ip = (O + 7) // 8 * 8, (I + 7) // 8 * 8
+    dev = x2.device
+    dyf = dy.float()
+    if relu:
+        dyf = dyf * (y > 0)
+    db = dyf.sum(0)
+    dyp = torch.zeros((B_, Op), dtype=BF16, device=dev); dyp[:, :O] = dyf
+    xp = torch.zeros((B_, Ip), dtype=BF16, device=dev); xp[:, :I] = x2
+    wp = torch.zeros((Op, Ip), dtype=BF16, device=dev); wp[:O, :I] = w
+    dx = gemm(dyp, wp, B_, Ip, Op, b_mn=True, lda=Op, ldb=Ip)[:, :I].contiguous() if need_dx else None
+    dwp = torch.empty((Op, Ip), dtype=torch.float32, device=dev)
+    gemm(dyp, xp, Op, Ip, B_, a_mn=True, b_mn=True, out=dwp, lda=Op, ldb=Ip, ldc=Ip)
+    dw = dwp[:O, :I]
+    if dw_out is not None:
+        dw_out.copy_(dw); dw = dw_out
+    if db_out is not None:
+        db_out.view(-1).copy_(db); db = db_out
+    return dx, dw, db
+
+
+# --------------------------------------------------------------------------- conv (NHWC, im2col + tcgen05 GEMM)
+def _out_hw(H, W, KH, KW, s, p):
+    return (H + 2 * p - KH) // s + 1, (W + 2 * p - KW) // s + 1
+
+
+def _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p):
+    N, H, W, Ct = x.shape
+    K = KH * KW * Cg
+    if KH == 1 and KW == 1 and s == 1 and p == 0 and c_off == 0 and Cg == Ct and Ct % 8 == 0:
+        return x.view(N * H * W, Ct), Ct, K                     # 1x1 conv: the activation IS the matrix
+    Kp = (K + 7) // 8 * 8
+    col = torch.empty((N * Ho * Wo, Kp), dtype=BF16, device=x.device)
+    L().im2col(x.data_ptr(), col.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+    return col, Kp, K
+
+
+def _w2d(w, K, Kp):
+    """OHWI bf16 weights as the GEMM's [O, Kp] K-major operand (zero-padded when K % 8 != 0)."""
+    O = w.shape[0]
+    w2 = _bf(w).reshape(O, K)
+    if Kp == K and w2.data_ptr() % 16 == 0:
+        return w2
+    wp = torch.empty((O, Kp), dtype=BF16, device=w.device)
+    L().pad_rows(w2.data_ptr(), wp.data_ptr(), O, K, K, Kp, _st(w))
+    return wp
+
+
+def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
+    N, H, W, Ct = x.shape
+    Og, KH, KW, _ = w.shape
+    Ho, Wo = y.shape[1], y.shape[2]
+    Ot = y.shape[3]
+    col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
+    w2 = _w2d(w, K, Kp)
+    M = N * Ho * Wo
+    yv = y.view(M, Ot)[:, o_off:o_off + Og]
+    gemm(col, w2, M, Og, K, out=yv, bias=b, bias_mode=1 if b is not None else 0, relu=relu, lda=Kp, ldb=Kp, ldc=Ot)
+
+
+def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True):
+    x = _bf(x).contiguous()
+    N, H, W, C = x.shape
+    O, KH, KW, Cg = w.shape
+    assert Cg * groups == C
+    Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
+    y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=x.device)
+    Og = O // groups
+    for g in range(groups):
+        _conv_fwd_group(x, w[g * Og:(g + 1) * Og], None if b is None else b[g * Og:(g + 1) * Og], y, g * Og, g * Cg, Cg,
+                        stride, pad, relu)
+    return y
+
+
+def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu):
+    x = _bf(x).contiguous()
+    N, H, W, C = x.shape
+    Og, KH, KW, Cg = w0.shape
+    Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
+    y = torch.empty((N, Ho, Wo, 2 * Og), dtype=BF16, device=x.device)
+    _conv_fwd_group(x, w0, b0, y, 0, 0, Cg, stride, pad, relu)
+    _conv_fwd_group(x, w1, b1, y, Og, Cg, Cg, stride, pad, relu)
+    return y
+
+
+def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out):
+    N, H, W, Ct = x.shape
+    Og, KH, KW, _ = w.shape
+    Ho, Wo, Ot = y.shape[1], y.shape[2], y.shape[3]
+    M = N * Ho * Wo
+    dev = x.device
+    dyv = dy.view(M, Ot)[:, o_off:o_off + Og]
+    yv = y.view(M, Ot)[:, o_off:o_off + Og]
+    dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
+    col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
+    dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
+    # wgrad: dW[Og, K] = dymᵀ[Og, M] · col[M, K]   (both operands MN-major, split-K over M)
+    gemm(dym, col, Og, K, M, a_mn=True, b_mn=True, out=dw.view(Og, K), lda=Og, ldb=Kp, ldc=K)
+    if need_dx:
+        w2 = _w2d(w, K, Kp)
+        one_by_one = (KH == 1 and KW == 1 and s == 1 and p == 0 and c_off == 0 and Cg == Ct)
+        if one_by_one:
+            gemm(dym, w2, M, Kp, Og, b_mn=True, out=dx.view(M, Ct), lda=Og, ldb=Kp, ldc=Ct)
+        else:
+            dcol = gemm(dym, w2, M, Kp, Og, b_mn=True, lda=Og, ldb=Kp)
+            L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+    return dw, db
+
+
+def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None):
+    x = _bf(x).contiguous()
+    dy = _bf(dy).contiguous()
+    N, H, W, C = x.shape
+    O, KH, KW, Cg = w.shape
+    if (Cg % 8 or O % 8) and need_dx:
+        raise RuntimeError("conv dgrad needs channel counts that are multiples of 8")
+    dx = torch.empty_like(x) if need_dx else None
+    Og = O // groups
+    if groups == 1:
+        dw, db = _conv_bwd_group(x, w, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, dw_out, db_out)
+        return dx, dw, db
+    dw = dw_out if dw_out is not None else torch.empty(tuple(w.shape), dtype=torch.float32, device=x.device)
+    db = db_out if db_out is not None else torch.empty(O, dtype=torch.float32, device=x.device)
+    for g in range(groups):
+        _conv_bwd_group(x, w[g * Og:(g + 1) * Og], y, dy, dx, g * Og, g * Cg, Cg, stride, pad, relu, need_dx,
+                        dw[g * Og:(g + 1) * Og], db[g * Og:(g + 1) * Og])
+    return dx, dw, db
+
+
+def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, outs=(None, None, None, None)):
+    x = _bf(x).contiguous()
+    dy = _bf(dy).contiguous()
+    Og, KH, KW, Cg = w0.shape
+    dx = torch.empty_like(x) if need_dx else None
+    dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1])
+    dw1, db1 = _conv_bwd_group(x, w1, y, dy, dx, Og, Cg, Cg, stride, pad, relu, need_dx, outs[2], outs[3])
+    return dx, (dw0, db0, dw1, db1)
+
+
+# --------------------------------------------------------------------------- pool / LRN / dropout / loss
+def pool2d_fwd(x, ksize, stride, pad, mode):
+    x = _bf(x).contiguous()
+    N, H, W, C = x.shape
+    Ho, Wo = _out_hw(H, W, ksize, ksize, stride, pad)
+    y = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+    is_max = mode == "max"
+    arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device) if is_max else None
+    L().pool_fwd(x.data_ptr(), y.data_ptr(), _p(arg), N, H, W, C, Ho, Wo, int(ksize), int(stride), int(pad), int(is_max), _st(x))
+    return y, arg
+
+
+def pool2d_bwd_arg(dy, arg, xshape, ksize, stride, pad, mode):
+    dy = _bf(dy).contiguous()
+    N, H, W, C = xshape
+    Ho, Wo = dy.shape[1], dy.shape[2]
+    dx = torch.empty(tuple(xshape), dtype=BF16, device=dy.device)
+    L().pool_bwd(dy.data_ptr(), _p(arg), dx.data_ptr(), N, H, W, C, Ho, Wo, int(ksize), int(stride), int(pad),
+                 int(mode == "max"), _st(dy))
+    return dx
+
+
+def lrn(x, n=5, k=2.0, alpha=1e-4, beta=0.75):
+    x = _bf(x).contiguous()
+    C = x.shape[-1]
+    y = torch.empty_like(x)
+    L().lrn_fwd(x.data_ptr(), y.data_ptr(), x.numel() // C, C, int(n), float(k), float(alpha), float(beta), _st(x))
+    return y, None
+
+
+def lrn_bwd(x, dy, n=5, k=2.0, alpha=1e-4, beta=0.75):
+    x = _bf(x).contiguous()
+    dy = _bf(dy).contiguous()
+    C = x.shape[-1]
+    dx = torch.empty_like(x)
+    L().lrn_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel() // C, C, int(n), float(k), float(alpha), float(beta), _st(x))
+    return dx
+
+
+def dropout_fwd(x, p_drop, layer_id):
+    from .functional import rng_state
+    x = _bf(x).contiguous()
+    y = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    step = step_counter(x.device)
+    L().dropout_fwd(x.data_ptr(), y.data_ptr(), mask.data_ptr(), x.numel(), float(p_drop), int(rng_state()["seed"]),
+                    int(layer_id), step.data_ptr(), _st(x))
+    return y, mask
+
+
+def dropout_bwd(dy, mask):
+    dy = _bf(dy).contiguous()
+    dx = torch.empty_like(dy)
+    L().dropout_bwd(dy.data_ptr(), mask.data_ptr(), dx.data_ptr(), dy.numel(), _st(dy))
+    return dx
+
+
+def softmax_xent(logits, labels, weight=1.0):
+    lg = _bf(logits).contiguous()
+    B_, C = lg.shape
+    labels = labels.contiguous()
+    assert labels.dtype == torch.int64
+    dl = torch.empty_like(lg)
+    rowstat = torch.empty((B_, 3), dtype=torch.float32, device=lg.device)
+    out3 = torch.empty(3, dtype=torch.float32, device=lg.device)
+    L().softmax_xent(lg.data_ptr(), labels.data_ptr(), dl.data_ptr(), rowstat.data_ptr(), out3.data_ptr(), B_, C, float(weight), _st(lg))
+    return out3[0], out3[1], out3[2], dl
+
+
+# --------------------------------------------------------------------------- loader kernel
+def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype=BF16, out=None, c_out=None):
+    x = x.contiguous()
+    N, H, W, C = x.shape
+    ch, cw = crop_hw
+    kind = {torch.uint8: 0, torch.bfloat16: 1, torch.float32: 2}[x.dtype]
+    mean = mean.float().contiguous()
+    mode = 0 if mean.numel() == 1 else (1 if mean.numel() == C else 2)
+    if mode == 2:
+        assert mean.numel() == H * W * C
+    Cout = c_out or C
+    if out is None:
+        out = torch.empty((N, ch, cw, Cout), dtype=out_dtype, device=x.device)
+    assert out.dtype in (BF16, torch.float32)
+    offsets = offsets.to(torch.int32).contiguous()
+    flips = flips.to(torch.uint8).contiguous()
+    L().crop_mirror_norm(x.data_ptr(), kind, mean.data_ptr(), mode, float(std_scale), out.data_ptr(), int(out.dtype == BF16),
+                         offsets.data_ptr(), flips.data_ptr(), N, H, W, C, ch, cw, Cout, _st(x))
+    return out
+
+
+# --------------------------------------------------------------------------- optimizer
+def _table(arena):
+    if not hasattr(arena, "_tab_cache"):
+        arena._tab_cache = (arena.group_lr_mult_np.tolist(), arena.group_wd_np.tolist(),
+                            [int(v) for v in arena.group_exch_np.tolist()])
+    return arena._tab_cache
+
+
+def sgd_flat(arena, g, lr, mu, nesterov, inv_k, lo, hi, only_local=False, only_exchanged=False):
+    """Fused momentum-SGD over arena elements [lo, hi).  ``lr`` is read from
+    ``arena.hyper[0]`` on the device (so a captured CUDA graph follows lr changes)."""
+    lrm, wd, ex = _table(arena)
+    filt = 1 if only_local else (2 if only_exchanged else 0)
+    H = arena.H
+    L().sgd_flat(arena.W.data_ptr(), g.data_ptr(), arena.U.data_ptr(), _p(H), arena.block_group.data_ptr(), lrm, wd, ex,
+                 arena.hyper.data_ptr(), float(mu), int(bool(nesterov)), float(inv_k), int(lo), int(hi), filt, _st(arena.W))

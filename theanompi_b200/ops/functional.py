@@ -182,15 +182,27 @@ def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride=1, pad=0, relu=True):
 class _PoolFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, ksize, stride, pad, mode):
-        y = _impl(x).pool2d(x, ksize, stride, pad, mode)
-        ctx.save_for_backward(x, y)
         ctx.cfg = (ksize, stride, pad, mode)
+        if x.is_cuda:
+            from . import cuda_impl
+            y, arg = cuda_impl.pool2d_fwd(x, ksize, stride, pad, mode)
+            ctx.xshape = tuple(x.shape)
+            ctx.has_arg = arg is not None
+            if arg is not None:
+                ctx.save_for_backward(arg)
+            return y
+        y = ref.pool2d(x, ksize, stride, pad, mode)
+        ctx.save_for_backward(x, y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        if dy.is_cuda:
+            from . import cuda_impl
+            arg = ctx.saved_tensors[0] if ctx.has_arg else None
+            return cuda_impl.pool2d_bwd_arg(dy, arg, ctx.xshape, *ctx.cfg), None, None, None, None
         x, y = ctx.saved_tensors
-        dx = _impl(x).pool2d_bwd(x, y, dy.contiguous(), *ctx.cfg)
+        dx = ref.pool2d_bwd(x, y, dy.contiguous(), *ctx.cfg)
         return dx, None, None, None, None
 
 

@@ -1,0 +1,401 @@
+"""Exchangers: the glue between a rule's runtime and the communication backend
+(ref ``theanompi/lib/exchanger.py``).
+
+``BSP_Exchanger``    (``exchanger.py:45-134``)  per-iteration exchange; strategy selection
+``EASGD_Exchanger``  (``:137-286``)             elastic push/pull against the center
+``ASGD_Exchanger``   (``:289-392``)             delta-accumulate variant (dead in the reference)
+``GOSGD_Exchanger``  (``:412-617``)             gossip push-sum merge with a random peer
+
+B200-native hot paths (no NCCL / MPI call on them):
+
+* BSP ``fused*`` strategies: ONE kernel family reads all peers' gradients over NVLink,
+  averages, applies weight-decay + momentum + lr, refreshes the bf16 compute shadow and
+  (two-shot / NVLS) pushes the updated slice to the peers; launched per bucket on a side
+  stream from the backward's grad-ready callbacks so it overlaps backward; part of the
+  captured CUDA graph.
+* EASGD: the worker's kernel computes ``d = α(w − c)`` against the center's memory mapped
+  over NVLink and updates BOTH sides in one pass (the reference does two full-model
+  broadcasts + an update sweep on each side).
+* GOSGD: the sender snapshots its weights locally and keeps training; the receiver's
+  kernel pulls the snapshot over NVLink and blends ``(α·w + α_s·b)/(α+α_s)`` in one pass.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import exchanger_strategy as ES
+
+FUSED = {"fused": ("auto", False), "fused16": ("auto", True), "oneshot": ("oneshot", False),
+         "oneshot16": ("oneshot", True), "twoshot": ("twoshot", False), "twoshot16": ("twoshot", True),
+         "nvls": ("nvls", False), "nvls16": ("nvls", True)}
+
+
+# --------------------------------------------------------------------------- p2p helpers (ref :10-33)
+def do_sendrecv(comm, glist, wlist, dest, group=None):
+    """Exchange the tensors of ``glist`` with ``dest`` into ``wlist`` (device buffers)."""
+    for g, w in zip(glist, wlist):
+        ops = [dist.P2POp(dist.isend, g.contiguous(), dest, group=group), dist.P2POp(dist.irecv, w, dest, group=group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+
+
+def do_send(comm, glist, dest, group=None):
+    for g in glist:
+        dist.send(g.contiguous(), dest, group=group)
+
+
+def do_recv(comm, wlist, src, group=None):
+    for w in wlist:
+        dist.recv(w, src, group=group)
+
+
+def remove_BN_params(param_list):
+    """Drop params named gamma/beta from the exchanged list (ref ``:35-43``)."""
+    return [p for p in param_list if getattr(p, "pname", None) not in ("gamma", "beta")]
+
+
+# =========================================================================== BSP
+class BSP_Exchanger(object):
+    def __init__(self, comm, gpucomm, exch_strategy, sync_type, ctx, model, nccl_group=None,
+                 bucket_bytes=None, overlap=True, comm_blocks=None):
+        self.comm, self.gpucomm = comm, gpucomm
+        self.size = comm.size
+        self.exch_strategy, self.sync_type, self.ctx, self.model = exch_strategy, sync_type, ctx, model
+        self.arena = getattr(model, "arena", None)
+        self.fused = exch_strategy in FUSED and self.size > 1
+        self.exch = None
+        self.overlap = overlap
+        self.comm_blocks = comm_blocks
+        self.bucket_bytes = bucket_bytes
+        self.nccl_group = nccl_group
+        if self.size == 1:
+            return
+        if self.fused:
+            if sync_type != "cdd":
+                raise ValueError("fused strategies implement the cdd (gradient) exchange")
+            if gpucomm is None:
+                raise RuntimeError("strategy %s needs the symmetric peer arena (GPUs of one node)" % exch_strategy)
+            self.algo, self.wire16 = FUSED[exch_strategy]
+            self._setup_buckets()
+            return
+        if sync_type == "cdd":
+            src, dst, avg = model.vels, model.vels2, False
+        elif sync_type == "avg":
+            src = dst = remove_BN_params(model.params)
+            avg = True
+        else:
+            raise ValueError("sync_type must be cdd or avg")
+        s = exch_strategy
+        if s == "ar":
+            self.exch = ES.Exch_allreduce(comm, avg=avg)
+        elif s == "nccl32":
+            self.exch = ES.Exch_nccl32(comm, nccl_group, avg=avg)
+        elif s == "nccl16":
+            self.exch = ES.Exch_nccl16(comm, nccl_group, avg=avg)
+        elif s == "asa32":
+            self.exch = ES.Exch_asa32(comm, avg=avg, group=nccl_group)
+        elif s == "asa16":
+            self.exch = ES.Exch_asa16(comm, avg=avg, group=nccl_group)
+        elif s == "copper":
+            self.exch = ES.Exch_copper(comm, avg=avg, group=nccl_group)
+        elif s == "copper16":
+            self.exch = ES.Exch_copper16(comm, avg=avg, group=nccl_group)
+        elif s == "swap":
+            self.exch = ES.Exch_swap(comm, group=nccl_group)
+            src = dst = remove_BN_params(model.params)       # fixes the undefined self.param_list
+        elif s == "p2p32":
+            if sync_type == "cdd":
+                self.exch = ES.Exch_p2p32(gpucomm, self.arena, model._send_region, "R", avg=False)
+            else:
+                self.exch = ES.Exch_p2p32(gpucomm, self.arena, "W", "W", avg=True)
+        else:
+            raise ValueError("unknown exch_strategy %r" % s)
+        self.exch.prepare(ctx, src, dst)
+
+    # ------------------------------------------------------------------ fused path
+    def _setup_buckets(self):
+        a = self.arena
+        bb = self.bucket_bytes or (a.numel * 4 if not self.overlap else 32 << 20)
+        self.buckets = a.make_buckets(bb) if self.overlap else [dict(lo=0, hi=a.numel, params=list(range(len(a.params))))]
+        self._pending = [0] * len(self.buckets)
+        self._bucket_of = {}
+        for bi, b in enumerate(self.buckets):
+            for pi in b["params"]:
+                self._bucket_of[pi] = bi
+        self._index_of = {id(p): i for i, p in enumerate(a.params)}
+        self.side = torch.cuda.Stream(device=a.device) if self.overlap else None
+        self._launched = 0
+        if self.overlap:
+            for p in a.params:
+                p.on_ready = self._on_ready
+            self._reset_pending()
+
+    def _reset_pending(self):
+        for bi, b in enumerate(self.buckets):
+            self._pending[bi] = len(b["params"])
+        self._launched = 0
+
+    def _launch_bucket(self, bi):
+        b, m = self.buckets[bi], self.model
+        mu = m.mu if m.use_momentum else 0.0
+        blocks = self.comm_blocks
+        if blocks is None and self.overlap:
+            blocks = 32 if (b["hi"] - b["lo"]) * 4 > (8 << 20) else 8
+        self.gpucomm.fused_allreduce_sgd(self.arena, b["lo"], b["hi"], mu, m.use_nesterov_momentum,
+                                         algo=self.algo, wire16=self.wire16, max_blocks=blocks)
+
+    def _on_ready(self, p):
+        """Called by a backward kernel wrapper right after it enqueued the gradient of ``p``."""
+        bi = self._bucket_of[self._index_of[id(p)]]
+        self._pending[bi] -= 1
+        # buckets must start in the SAME order on every rank (device-side barriers pair up by launch order)
+        while self._launched < len(self.buckets) and self._pending[self._launched] == 0:
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                self._launch_bucket(self._launched)
+            self._launched += 1
+
+    def fused_step(self):
+        """The model's *step tail*: everything left of the exchange + update, then join."""
+        if self.overlap:
+            # parameters that did not go through an on_ready callback (e.g. unused) flush here
+            cur = torch.cuda.current_stream()
+            while self._launched < len(self.buckets):
+                self.side.wait_stream(cur)
+                with torch.cuda.stream(self.side):
+                    self._launch_bucket(self._launched)
+                self._launched += 1
+            cur.wait_stream(self.side)
+            self._reset_pending()
+        else:
+            self._launch_bucket(0)
+
+    # ------------------------------------------------------------------ the per-iteration call
+    def exchange(self, recorder):
+        """Barrier timed as *sync*, collective as *comm* (ref ``:120-134``); then the post
+        update runs immediately.  For fused strategies both already
+        happened inside the step (device-side barrier + fused kernel): nothing to launch."""
+        if self.size == 1:
+            return
+        if self.fused:
+            return
+        recorder.start()
+        self.comm.Barrier()
+        recorder.end("sync")
+        recorder.start()
+        self.exch.exchange()
+        if self.sync_type == "cdd":
+            self.model.descent_vel()
+        elif self.arena is not None and self.exch_strategy != "p2p32":
+            self.arena.refresh_shadow()
+        recorder.end("comm")
+
+
+# =========================================================================== EASGD
+class EASGD_Exchanger(object):
+    """Elastic averaging against the center.
+
+    ``etype='server'`` owns the center (its model's arena W); ``etype='worker'`` owns a
+    replica.  GPU path: worker-side fused kernel on the peer-mapped center.  CPU path:
+    the two sides swap flat copies (gloo) and apply the reference's update functions
+    (``exchanger.py:188-211``): server ``g += α(w−g)``, worker ``w −= α(w−g)``."""
+
+    def __init__(self, alpha, param_list, etype, comm=None, gpucomm=None, arena=None, server_rank=0, group=None):
+        self.alpha, self.etype = alpha, etype
+        self.param_list = param_list
+        self.comm, self.gpucomm, self.arena, self.group = comm, gpucomm, arena, group
+        self.server_rank = server_rank
+        self.peer = None                       # server: rank of the worker being served
+        self.device = arena.W.device if arena is not None else param_list[0].device
+        self.use_p2p = gpucomm is not None and self.device.type == "cuda"
+        if not self.use_p2p:
+            n = arena.numel if arena is not None else sum(p.numel() for p in param_list)
+            self.mirror = torch.zeros(n, dtype=torch.float32, device=self.device)
+
+    def _flat(self):
+        if self.arena is not None:
+            return self.arena.W
+        return torch.cat([p.detach().reshape(-1) for p in self.param_list])
+
+    def _unflat(self, flat):
+        if self.arena is not None:
+            if flat.data_ptr() != self.arena.W.data_ptr():
+                self.arena.W.copy_(flat)
+            self.arena.refresh_shadow()
+            return
+        off = 0
+        with torch.no_grad():
+            for p in self.param_list:
+                p.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+
+    def exchange(self):
+        if self.use_p2p:
+            if self.etype == "worker":
+                from ..ops import native
+                a, gc = self.arena, self.gpucomm
+                center = gc.peer_region(self.server_rank, a.layout["W"], a.numel)
+                native.require().easgd_elastic(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(),
+                                               float(self.alpha), a.numel, gc._blocks(None), gc._stream())
+                torch.cuda.current_stream(self.device).synchronize()
+            return
+        other = self.peer if self.etype == "server" else self.server_rank
+        mine = self._flat().contiguous()
+        ops = [dist.P2POp(dist.isend, mine, other, group=self.group), dist.P2POp(dist.irecv, self.mirror, other, group=self.group)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        with torch.no_grad():
+            if self.etype == "server":
+                new = mine + self.alpha * (self.mirror - mine)          # g += α(w − g)
+            else:
+                new = mine - self.alpha * (mine - self.mirror)          # w −= α(w − g)
+            self._unflat(new)
+
+    def copy_to_local(self):
+        """Worker ← center (before/after validation and at stop, ref ``:264-286``)."""
+        if self.use_p2p:
+            if self.etype == "worker":
+                from ..ops import native
+                a, gc = self.arena, self.gpucomm
+                center = gc.peer_region(self.server_rank, a.layout["W"], a.numel)
+                native.require().copy_flat(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(),
+                                           a.numel, gc._blocks(None), gc._stream())
+                torch.cuda.current_stream(self.device).synchronize()
+            return
+        if self.etype == "server":
+            dist.send(self._flat().contiguous(), self.peer, group=self.group)
+        else:
+            dist.recv(self.mirror, self.server_rank, group=self.group)
+            self._unflat(self.mirror.clone())
+
+
+# =========================================================================== ASGD (delta push)
+class ASGD_Exchanger(object):
+    """Server ``g += Δ``; worker ``w = g_new; Δ = 0`` where Δ = w − w_at_last_sync
+    (ref ``exchanger.py:289-392``; no reference rule uses it — kept for the ``ASGD`` stub)."""
+
+    def __init__(self, param_list, etype, comm=None, arena=None, server_rank=0, group=None):
+        self.etype, self.comm, self.arena, self.server_rank, self.group = etype, comm, arena, server_rank, group
+        self.param_list = param_list
+        self.peer = None
+        n = arena.numel if arena is not None else sum(p.numel() for p in param_list)
+        dev = arena.W.device if arena is not None else param_list[0].device
+        self.buf = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.last = self._flat().clone()
+
+    _flat = EASGD_Exchanger._flat
+    _unflat = EASGD_Exchanger._unflat
+
+    def exchange(self):
+        if self.etype == "server":
+            dist.recv(self.buf, self.peer, group=self.group)             # Δ from the worker
+            new = self._flat() + self.buf
+            self._unflat(new)
+            dist.send(self._flat().contiguous(), self.peer, group=self.group)
+        else:
+            delta = (self._flat() - self.last).contiguous()
+            dist.send(delta, self.server_rank, group=self.group)
+            dist.recv(self.buf, self.server_rank, group=self.group)
+            self._unflat(self.buf.clone())
+            self.last = self._flat().clone()
+
+
+# =========================================================================== GOSGD
+class GOSGD_Exchanger(object):
+    TAG_REQ, TAG_ACK = 700, 703
+
+    def __init__(self, comm, gpucomm, model, p=0.01, seed=None, group=None):
+        self.comm, self.gpucomm, self.model, self.p = comm, gpucomm, model, p
+        self.rank, self.size = comm.rank, comm.size
+        self.arena = model.arena
+        self.alpha = 1.0 / self.size                              # push-sum weight (ref :430)
+        self.rs = np.random.RandomState(seed if seed is not None else (1000 + 7919 * self.rank))
+        self.group = group
+        self.device = self.arena.W.device
+        self.use_p2p = gpucomm is not None and self.device.type == "cuda"
+        self._unacked = 0
+        self._pending_sends = []
+        if not self.use_p2p:
+            self.b = torch.zeros(self.arena.numel, dtype=torch.float32, device=self.device)
+            self.snap = torch.zeros_like(self.b)
+        self.n_merged = 0
+        self.n_pushed = 0
+
+    # ---- Bernoulli draw + uniform peer (ref :586-617)
+    def draw(self):
+        return self.rs.binomial(1, self.p) == 1
+
+    def choose(self):
+        if self.size < 2:
+            return None
+        d = self.rs.randint(0, self.size - 1)
+        return d if d < self.rank else d + 1
+
+    # ---- receiver side
+    def process_messages(self, count_arr=None):
+        """Drain inbound pushes: pull the sender's snapshot, blend, add its weight
+        (ref ``:484-535``).  ``count_arr`` is merged element-wise (max) instead of being
+        overwritten by the sender's view."""
+        while self.comm.iprobe(tag=self.TAG_ACK):
+            self.comm.recv(tag=self.TAG_ACK)
+            self._unacked -= 1
+        merged = 0
+        while self.comm.iprobe(tag=self.TAG_REQ):
+            msg = self.comm.recv(tag=self.TAG_REQ)
+            src, a_src = msg["src"], float(msg["alpha"])
+            if count_arr is not None and msg.get("count") is not None:
+                np.maximum(count_arr, np.asarray(msg["count"]), out=count_arr)
+            self._merge_params_from(src, a_src)
+            self.alpha += a_src
+            self.comm.send(self.rank, src, tag=self.TAG_ACK)
+            merged += 1
+        self.n_merged += merged
+        return merged
+
+    def _merge_params_from(self, src, a_src):
+        a = self.arena
+        if self.use_p2p:
+            from ..ops import native
+            gc = self.gpucomm
+            b = gc.peer_region(src, a.layout["R"], a.numel)       # sender's snapshot over NVLink
+            native.require().gosgd_merge(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, b.data_ptr(),
+                                         float(self.alpha), float(a_src), a.numel, gc._blocks(None), gc._stream())
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            dist.recv(self.b, src, group=self.group)
+            from ..ops import reference as ref
+            with torch.no_grad():
+                ref.gosgd_merge(a.W, self.b, self.alpha, a_src)
+            a.refresh_shadow()
+
+    # ---- sender side
+    def push_message(self, dest, count_arr=None):
+        """Snapshot my weights, halve my push-sum weight, notify ``dest`` and keep training
+        (ref ``:538-584`` blocks inside ncclBcast until the receiver joins)."""
+        while self._unacked > 0:                                   # my snapshot buffer is still being pulled
+            self.process_messages(count_arr)
+        a = self.arena
+        if self.use_p2p:
+            from ..ops import native
+            gc = self.gpucomm
+            native.require().copy_flat(a.R.data_ptr(), 0, a.W.data_ptr(), a.numel, gc._blocks(None), gc._stream())
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            self.snap.copy_(a.W)
+        self.alpha *= 0.5
+        self.comm.send({"src": self.rank, "alpha": self.alpha,
+                        "count": None if count_arr is None else np.asarray(count_arr).tolist()}, dest, tag=self.TAG_REQ)
+        self._unacked += 1
+        if not self.use_p2p:
+            self._pending_sends = [w for w in self._pending_sends if not w.is_completed()]
+            self._pending_sends.append(dist.isend(self.snap, dest, group=self.group))
+        self.n_pushed += 1
+
+    def finish(self):
+        """Serve inbound pushes until all of mine are acknowledged (clean shutdown)."""
+        while self._unacked > 0:
+            self.process_messages(None)
+        for w in self._pending_sends:
+            w.wait()

@@ -36,6 +36,11 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.doc() = "theanompi_b200 native sm_100a kernels and peer-memory runtime";
   m.def("launch_count", [] { return (unsigned long long)g_launch_count.load(); });
   m.def("reset_launch_count", [] { g_launch_count.store(0); });
+  m.def("capture_status", [](ptr_t st) {
+    cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+    cudaError_t e = cudaStreamIsCapturing(S(st), &s);
+    return py::make_tuple((int)e, (int)s);
+  });
   m.attr("ARENA_BLOCK") = kArenaBlock;
   m.attr("MAX_RANKS") = kMaxRanks;
   m.attr("MAX_COMM_BLOCKS") = kMaxCommBlocks;

@@ -140,7 +140,7 @@ void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group,
   int grid = (int)std::min<long long>(nb, (long long)sm_count() * 8);
   sgd_flat_kernel<<<grid, kThreads, 0, st>>>((float*)W, (const float*)G, (float*)U, (__nv_bfloat16*)H, (const uint8_t*)block_group, tab,
                                              (const float*)lr_ptr, mu, nesterov, inv_k, lo / kArenaBlock, hi / kArenaBlock, filter);
-  count_launch(); TMPI_CHECK_LAUNCH("sgd_flat");
+  count_launch(); TMPI_CHECK_LAUNCH("sgd_flat"); ::tmpi::check_capture(st, "sgd_flat");
 }
 
 // ============================================================================ fused collectives
@@ -282,7 +282,7 @@ void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStrea
     const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
     fused_twoshot_sgd_kernel<<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, algo == 2 ? 1 : 0);
   }
-  count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd");
+  count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd"); ::tmpi::check_capture(st, "fused_allreduce_sgd");
 }
 
 // ============================================================================ plain flat allreduce (sum * scale) src region → dst region
@@ -350,14 +350,14 @@ void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t 
   if (algo == 2 && a.ctx.mc_arena == nullptr) throw std::runtime_error("allreduce_flat: NVLS requested without a multicast mapping");
   if (algo == 0) allreduce_oneshot_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
   else allreduce_twoshot_kernel<<<pick_grid((nb + a.ctx.world - 1) / a.ctx.world, max_blocks), kThreads, 0, st>>>(a, algo == 2 ? 1 : 0);
-  count_launch(); TMPI_CHECK_LAUNCH("allreduce_flat");
+  count_launch(); TMPI_CHECK_LAUNCH("allreduce_flat"); ::tmpi::check_capture(st, "allreduce_flat");
 }
 
 // standalone device barrier (tests / stream alignment)
 __global__ void barrier_kernel(const CommCtx c) { block_barrier(c); }
 void device_barrier(const CommCtx& c, cudaStream_t st) {
   barrier_kernel<<<1, 32, 0, st>>>(c);
-  count_launch(); TMPI_CHECK_LAUNCH("device_barrier");
+  count_launch(); TMPI_CHECK_LAUNCH("device_barrier"); ::tmpi::check_capture(st, "device_barrier");
 }
 
 // ============================================================================ EASGD elastic exchange (worker side, center over NVLink)
@@ -381,7 +381,7 @@ void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
   easgd_elastic_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (float*)center, alpha, nb);
-  count_launch(); TMPI_CHECK_LAUNCH("easgd_elastic");
+  count_launch(); TMPI_CHECK_LAUNCH("easgd_elastic"); ::tmpi::check_capture(st, "easgd_elastic");
 }
 
 // dst = src (+ bf16 shadow) over peer memory: EASGD copy_to_local, GOSGD push into the peer's mailbox region
@@ -399,7 +399,7 @@ void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blo
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
   copy_flat_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)dst, (__nv_bfloat16*)dst_h, (const float*)src, nb);
-  count_launch(); TMPI_CHECK_LAUNCH("copy_flat");
+  count_launch(); TMPI_CHECK_LAUNCH("copy_flat"); ::tmpi::check_capture(st, "copy_flat");
 }
 
 // ============================================================================ GOSGD merge:  w ← (a_self·w + a_src·b) / (a_self + a_src)
@@ -422,7 +422,7 @@ void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, lon
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
   gosgd_merge_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (const float*)b, a_self, a_src, nb);
-  count_launch(); TMPI_CHECK_LAUNCH("gosgd_merge");
+  count_launch(); TMPI_CHECK_LAUNCH("gosgd_merge"); ::tmpi::check_capture(st, "gosgd_merge");
 }
 
 // ============================================================================ reference kernels K1..K5 (legacy strategies)
@@ -440,7 +440,7 @@ void cast_flat(const void* src, void* dst, long long n, int kind, cudaStream_t s
     case 3: cast_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n); break;
     default: throw std::runtime_error("cast_flat: bad kind");
   }
-  count_launch(); TMPI_CHECK_LAUNCH("cast_flat");
+  count_launch(); TMPI_CHECK_LAUNCH("cast_flat"); ::tmpi::check_capture(st, "cast_flat");
 }
 
 // K2/K3 sumfloats / sumhalfs with the reference's loop bug fixed: dst[i] = Σ_j src[i + chunk*j], fp32 accumulate
@@ -456,7 +456,7 @@ void sum_chunks(const void* src, void* dst, long long chunk, int nchunks, int is
   const int g = (int)std::min<long long>((chunk + 255) / 256, (long long)sm_count() * 16);
   if (is_half) sum_chunks_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, (__half*)dst, chunk, nchunks);
   else sum_chunks_kernel<float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, chunk, nchunks);
-  count_launch(); TMPI_CHECK_LAUNCH("sum_chunks");
+  count_launch(); TMPI_CHECK_LAUNCH("sum_chunks"); ::tmpi::check_capture(st, "sum_chunks");
 }
 
 // K4/K5 vecadd / vecaddhalf: cur[i] += tmp[i]
@@ -469,7 +469,7 @@ void vecadd(void* cur, const void* tmp, long long n, int is_half, cudaStream_t s
   const int g = (int)std::min<long long>((n + 255) / 256, (long long)sm_count() * 16);
   if (is_half) vecadd_kernel<__half><<<g, 256, 0, st>>>((__half*)cur, (const __half*)tmp, n);
   else vecadd_kernel<float><<<g, 256, 0, st>>>((float*)cur, (const float*)tmp, n);
-  count_launch(); TMPI_CHECK_LAUNCH("vecadd");
+  count_launch(); TMPI_CHECK_LAUNCH("vecadd"); ::tmpi::check_capture(st, "vecadd");
 }
 
 }  // namespace tmpi

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <atomic>
 #include <stdexcept>
 #include <string>
@@ -20,6 +21,18 @@ inline void check_cuda(cudaError_t e, const char* what) {
   }
 }
 #define TMPI_CHECK_LAUNCH(name) ::tmpi::check_cuda(cudaGetLastError(), name)
+
+// TMPI_DEBUG_CAPTURE=1: after every launch verify that an ongoing stream capture is still valid and name the
+// first op that invalidated it (CUDA only reports "a previous error" at capture end).
+inline void check_capture(cudaStream_t st, const char* name) {
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("TMPI_DEBUG_CAPTURE"); dbg = (e && e[0] == '1') ? 1 : 0; }
+  if (!dbg) return;
+  cudaStreamCaptureStatus s = cudaStreamCaptureStatusNone;
+  cudaError_t e = cudaStreamIsCapturing(st, &s);
+  if (e != cudaSuccess || s == cudaStreamCaptureStatusInvalidated)
+    throw std::runtime_error(std::string("tmpi_native: stream capture invalidated at/before ") + name + ": " + cudaGetErrorString(e));
+}
 
 constexpr int kArenaBlock = 1024;   // must match parallel/arena.py BLOCK
 constexpr int kMaxGroups = 8;

@@ -339,7 +339,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits);
   gemm_bf16_tcgen05<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   count_launch();
-  TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05");
+  TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
 }
 
 }  // namespace gemm

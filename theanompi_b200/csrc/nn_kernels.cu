@@ -101,7 +101,7 @@ void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, floa
     case 4: lrn_fwd_kernel<4><<<grid_for(total, B), B, 0, st>>>(X, Y, rows, C, k, alpha, beta); break;
     default: throw std::runtime_error("lrn: window n must be 3,5,7 or 9");
   }
-  count_launch(); TMPI_CHECK_LAUNCH("lrn_fwd");
+  count_launch(); TMPI_CHECK_LAUNCH("lrn_fwd"); ::tmpi::check_capture(st, "lrn_fwd");
 }
 
 void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st) {
@@ -117,7 +117,7 @@ void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int
     case 4: lrn_bwd_kernel<4><<<grid_for(total, B), B, 0, st>>>(X, DY, DX, rows, C, k, alpha, beta); break;
     default: throw std::runtime_error("lrn: window n must be 3,5,7 or 9");
   }
-  count_launch(); TMPI_CHECK_LAUNCH("lrn_bwd");
+  count_launch(); TMPI_CHECK_LAUNCH("lrn_bwd"); ::tmpi::check_capture(st, "lrn_bwd");
 }
 
 // ============================================================================ pooling
@@ -263,7 +263,7 @@ void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int
   long long total = (long long)N * Ho * Wo * (C / 8);
   if (is_max) maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)arg, g);
   else avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
-  count_launch(); TMPI_CHECK_LAUNCH("pool_fwd");
+  count_launch(); TMPI_CHECK_LAUNCH("pool_fwd"); ::tmpi::check_capture(st, "pool_fwd");
 }
 
 void pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st) {
@@ -271,7 +271,7 @@ void pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, in
   long long total = (long long)N * H * W * (C / 8);
   if (is_max) maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)arg, (__nv_bfloat16*)dx, g);
   else avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, g);
-  count_launch(); TMPI_CHECK_LAUNCH("pool_bwd");
+  count_launch(); TMPI_CHECK_LAUNCH("pool_bwd"); ::tmpi::check_capture(st, "pool_bwd");
 }
 
 // ============================================================================ dropout (Philox4x32-10)
@@ -330,15 +330,15 @@ void dropout_fwd(const void* x, void* y, void* mask, long long n, float p_drop, 
   if (n % 8) throw std::runtime_error("dropout: numel must be a multiple of 8");
   dropout_fwd_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)mask, n / 8, p_drop, seed,
                                                            (uint32_t)layer, (const unsigned long long*)step);
-  count_launch(); TMPI_CHECK_LAUNCH("dropout_fwd");
+  count_launch(); TMPI_CHECK_LAUNCH("dropout_fwd"); ::tmpi::check_capture(st, "dropout_fwd");
 }
 void dropout_bwd(const void* dy, const void* mask, void* dx, long long n, cudaStream_t st) {
   dropout_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)mask, (__nv_bfloat16*)dx, n / 8);
-  count_launch(); TMPI_CHECK_LAUNCH("dropout_bwd");
+  count_launch(); TMPI_CHECK_LAUNCH("dropout_bwd"); ::tmpi::check_capture(st, "dropout_bwd");
 }
 void advance_step(void* step, cudaStream_t st) {
   advance_step_kernel<<<1, 32, 0, st>>>((unsigned long long*)step);
-  count_launch(); TMPI_CHECK_LAUNCH("advance_step");
+  count_launch(); TMPI_CHECK_LAUNCH("advance_step"); ::tmpi::check_capture(st, "advance_step");
 }
 
 // ============================================================================ softmax + NLL + errors + dlogits
@@ -409,9 +409,9 @@ __global__ void rowstat_mean_kernel(const float* __restrict__ rowstat, float* __
 
 void softmax_xent(const void* logits, const void* labels, void* dlogits, void* rowstat, void* out3, int B, int C, float weight, cudaStream_t st) {
   softmax_xent_kernel<<<B, 256, 0, st>>>((const __nv_bfloat16*)logits, (const long long*)labels, (__nv_bfloat16*)dlogits, (float*)rowstat, C, weight / (float)B);
-  count_launch(); TMPI_CHECK_LAUNCH("softmax_xent");
+  count_launch(); TMPI_CHECK_LAUNCH("softmax_xent"); ::tmpi::check_capture(st, "softmax_xent");
   rowstat_mean_kernel<<<1, 256, 0, st>>>((const float*)rowstat, (float*)out3, B, weight);
-  count_launch(); TMPI_CHECK_LAUNCH("rowstat_mean");
+  count_launch(); TMPI_CHECK_LAUNCH("rowstat_mean"); ::tmpi::check_capture(st, "rowstat_mean");
 }
 
 // ============================================================================ ReLU mask + bias gradient
@@ -477,7 +477,7 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
   else if (relu) relu_bias_bwd_kernel<true, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
   else if (write) relu_bias_bwd_kernel<false, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
   else relu_bias_bwd_kernel<false, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
-  count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd");
+  count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd"); ::tmpi::check_capture(st, "relu_bias_bwd");
 }
 
 // ============================================================================ im2col / col2im (NHWC, bf16)
@@ -568,7 +568,7 @@ void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, 
     long long total = M * (KH * KW + 1);
     im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
   }
-  count_launch(); TMPI_CHECK_LAUNCH("im2col");
+  count_launch(); TMPI_CHECK_LAUNCH("im2col"); ::tmpi::check_capture(st, "im2col");
 }
 
 void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
@@ -577,7 +577,7 @@ void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off
   ConvGeom g{N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, KH * KW * Cg};
   long long total = (long long)N * H * W * (Cg / 8);
   col2im_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, g);
-  count_launch(); TMPI_CHECK_LAUNCH("col2im");
+  count_launch(); TMPI_CHECK_LAUNCH("col2im"); ::tmpi::check_capture(st, "col2im");
 }
 
 // ============================================================================ small utility kernels
@@ -591,7 +591,7 @@ __global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bflo
 }
 void pad_rows(const void* src, void* dst, long long rows, int cols, long long src_ld, long long dst_ld, cudaStream_t st) {
   pad_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols, src_ld, dst_ld);
-  count_launch(); TMPI_CHECK_LAUNCH("pad_rows");
+  count_launch(); TMPI_CHECK_LAUNCH("pad_rows"); ::tmpi::check_capture(st, "pad_rows");
 }
 
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C) {
@@ -605,7 +605,7 @@ __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __n
 void transpose_bf16(const void* src, void* dst, int R, int C, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_bf16_kernel<<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, C);
-  count_launch(); TMPI_CHECK_LAUNCH("transpose_bf16");
+  count_launch(); TMPI_CHECK_LAUNCH("transpose_bf16"); ::tmpi::check_capture(st, "transpose_bf16");
 }
 
 // ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32
@@ -644,7 +644,7 @@ void crop_mirror_norm(const void* x, int in_kind /*0 u8, 1 bf16, 2 f32*/, const 
   else if (in_kind == 1) { if (out_bf16) CMN(__nv_bfloat16, __nv_bfloat16); else CMN(__nv_bfloat16, float); }
   else { if (out_bf16) CMN(float, __nv_bfloat16); else CMN(float, float); }
 #undef CMN
-  count_launch(); TMPI_CHECK_LAUNCH("crop_mirror_norm");
+  count_launch(); TMPI_CHECK_LAUNCH("crop_mirror_norm"); ::tmpi::check_capture(st, "crop_mirror_norm");
 }
 
 }  // namespace tmpi

@@ -84,6 +84,7 @@ class ModelBase(object):
         self.val_iter_fn = None
         self._graph = None
         self._graph_out = None
+        self._gstream = None
         self._warm = 0
         self._tail = None
         self.exchanger = None          # set by the BSP worker for fused / overlapped exchange
@@ -141,6 +142,7 @@ class ModelBase(object):
     # ------------------------------------------------------------------ step functions
     def _fwd_bwd_eager(self):
         cost, err, err5 = self.loss(self.x_in, self.y_in)
+        self._dbg_capture("forward")
         cost.backward()
         return cost.detach(), err.detach()
 
@@ -157,20 +159,43 @@ class ModelBase(object):
         if not self.use_graph:
             return self._step_body()
         if self._graph is None:
-            if self._warm < 2:                       # eager warm-up before capture
+            if self._gstream is None:
+                self._gstream = torch.cuda.Stream(device=self.device)
+            if self._warm < 2:
+                # Eager warm-up ON THE CAPTURE STREAM: autograd caches each leaf's AccumulateGrad node together
+                # with the stream that was current when it was first built; if that were the default stream the
+                # engine would make the capturing stream wait on uncaptured work at the end of backward
+                # (cudaErrorStreamCaptureIsolation).
                 self._warm += 1
-                return self._step_body()
+                cur = torch.cuda.current_stream(self.device)
+                self._gstream.wait_stream(cur)
+                with torch.cuda.stream(self._gstream):
+                    out = self._step_body()
+                cur.wait_stream(self._gstream)
+                return out
             self._capture()
         self._graph.replay()
         return self._graph_out
 
     def _step_body(self):
         out = self._fwd_bwd_eager()
+        self._dbg_capture("forward+backward")
         if self._tail is not None:
             with torch.no_grad():
                 self._tail()
+            self._dbg_capture("step tail")
         self._after_step()
         return out
+
+    def _dbg_capture(self, where):
+        """TMPI_DEBUG_CAPTURE=1: name the stage that invalidated an ongoing CUDA-graph capture."""
+        import os
+        if not self.cuda or os.environ.get("TMPI_DEBUG_CAPTURE") != "1":
+            return
+        from ..ops import native
+        err, status = native.require().capture_status(torch.cuda.current_stream(self.device).cuda_stream)
+        if err != 0 or status == 2:
+            raise RuntimeError("CUDA graph capture invalidated during %s (err %d status %d)" % (where, err, status))
 
     def _after_step(self):
         if self.cuda:
@@ -182,11 +207,21 @@ class ModelBase(object):
     def _capture(self):
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        s = torch.cuda.Stream()
+        s = self._gstream
         s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
-                out = self._step_body()
+        inner = None
+        try:
+            with torch.cuda.stream(s):
+                with torch.cuda.graph(g, stream=s, capture_error_mode="thread_local"):
+                    try:
+                        out = self._step_body()
+                    except BaseException as e:       # capture_end would mask it with "invalidated"
+                        inner = e
+                        raise
+        except Exception:
+            if inner is not None:
+                raise inner
+            raise
         torch.cuda.current_stream().wait_stream(s)
         self._graph, self._graph_out = g, out
 

@@ -31,7 +31,7 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 
 template <int BN> struct Cfg {
-  static constexpr int STAGES = (BN == 128) ? 5 : (BN == 64 ? 6 : 8);
+  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);   // <= ~100 KB: two CTAs co-reside per SM
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -136,7 +136,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 
 // ------------------------------------------------------------------ the kernel
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(NUM_THREADS, 2)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -228,14 +228,22 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM → registers → global =====================
+    // ===================== epilogue: TMEM → registers → (smem staging) → global =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int m = m0 + 32 * q + lane;
+    const int row = 32 * q + lane;                 // row inside the tile
+    const int m = m0 + row;
     const bool m_ok = m < p.M;
     float bias_m = 0.f;
     if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
+    // Fast path: the whole tile is in range and 16-byte aligned → stage it through the (now idle) operand smem so
+    // global stores are full coalesced 16 B vectors along the row instead of one strided row chunk per lane.
+    const int esz = p.out_bf16 ? 2 : 4;
+    const bool staged = !p.atomic_out && (n0 + BN <= p.N) && (((long long)p.ldc * esz) % 16 == 0) &&
+                        ((reinterpret_cast<uintptr_t>(p.C) + (long long)n0 * esz) % 16 == 0);
+    const uint32_t pitch = (uint32_t)(BN * esz + 16);                      // +16 B: conflict-free v4 stores
+    uint8_t* stage_ptr = smem_raw + (smem_base - smem_u32(smem_raw));
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -243,7 +251,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
       tmem_ld_wait();
       const int nb = n0 + 32 * c;
-      if (!m_ok || nb >= p.N) continue;
+      if (!staged && (!m_ok || nb >= p.N)) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
@@ -252,6 +260,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         else if (p.bias_mode == 2) { x += bias_m; }
         if (p.relu) x = fmaxf(x, 0.f);
         v[j] = x;
+      }
+      if (staged) {
+        uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)(32 * c) * esz;
+        if (p.out_bf16) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        continue;
       }
       const bool full = (nb + 32 <= p.N);
       if (p.atomic_out) {
@@ -275,6 +294,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+        }
+      }
+    }
+    if (staged) {
+      // each warp re-reads only the 32 rows it staged itself → a warp-level sync is enough
+      __syncwarp();
+      const int vec_per_row = (BN * esz) / 16;                 // 16-byte vectors per tile row
+      const int rows_per_it = 32 / vec_per_row > 0 ? 32 / vec_per_row : 1;
+      uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)n0 * esz;
+      if (vec_per_row <= 32) {
+        const int lr = lane / vec_per_row, lv = lane % vec_per_row;
+        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
+          const int rr = 32 * q + r0 + lr;
+          if (lr < rows_per_it && m0 + rr < p.M) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + (size_t)rr * pitch + (size_t)lv * 16);
+            *reinterpret_cast<uint4*>(gbase + (long long)(m0 + rr) * p.ldc * esz + (long long)lv * 16) = val;
+          }
         }
       }
     }

@@ -525,6 +525,46 @@ __global__ void im2col_scalar_kernel(const __nv_bfloat16* __restrict__ x, __nv_b
   for (int c = 0; c < g.Cg; ++c) dst[c] = ok ? src[c] : f_to_bf16(0.f);
 }
 
+// small-C path (conv1: C = 3): one CTA per (image, output row).  The KH input rows the output row needs are staged in
+// shared memory with coalesced loads; the CTA then emits its Wo consecutive col rows (one contiguous Wo*ldcol span)
+// as 16-byte vectors — each col row is KH runs of KW*Cg contiguous input elements.
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
+  extern __shared__ __nv_bfloat16 rows[];                  // [KH][W*Cg]
+  const int n = blockIdx.x / g.Ho, ho = blockIdx.x % g.Ho;
+  const int rowlen = g.W * g.Cg;
+  for (int i = threadIdx.x; i < g.KH * rowlen; i += blockDim.x) {
+    const int kh = i / rowlen, e = i % rowlen;
+    const int h = ho * g.s - g.p + kh;
+    __nv_bfloat16 v = f_to_bf16(0.f);
+    if (h >= 0 && h < g.H) {
+      const int w = e / g.Cg, c = e % g.Cg;
+      v = x[(((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off + c];
+    }
+    rows[i] = v;
+  }
+  __syncthreads();
+  const int run = g.KW * g.Cg;                             // contiguous elements per (kh)
+  const int vec_per_row = (int)(g.ldcol >> 3);
+  __nv_bfloat16* out = col + ((long long)n * g.Ho + ho) * g.Wo * g.ldcol;
+  for (int i = threadIdx.x; i < g.Wo * vec_per_row; i += blockDim.x) {
+    const int wo = i / vec_per_row, e0 = (i % vec_per_row) * 8;
+    const int xbase = (wo * g.s - g.p) * g.Cg;              // may be negative with padding
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + j;
+      __nv_bfloat16 t = f_to_bf16(0.f);
+      if (e < g.K) {
+        const int kh = e / run, r = e % run;
+        const int xi = xbase + r;
+        if (xi >= 0 && xi < rowlen) t = rows[kh * rowlen + xi];
+      }
+      v[j] = t;
+    }
+    *reinterpret_cast<uint4*>(out + (long long)wo * g.ldcol + e0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
 // dx[n,h,w,c_off+c] = sum over (kh,kw) with (h+p-kh)%s==0, (w+p-kw)%s==0 of dcol[m(n,ho,wo), (kh*KW+kw)*Cg + c]
 __global__ void col2im_vec8_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, ConvGeom g) {
   const int cvn = g.Cg >> 3;
@@ -564,6 +604,8 @@ void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, 
   if (Cg % 8 == 0 && c_off % 8 == 0 && Ctot % 8 == 0 && ldcol % 8 == 0) {
     long long total = M * KH * KW * (Cg / 8);
     im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
+  } else if (ldcol % 8 == 0 && (size_t)KH * W * Cg * 2 <= 48 * 1024) {
+    im2col_rows_kernel<<<N * Ho, 256, (size_t)KH * W * Cg * 2, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
   } else {
     long long total = M * (KH * KW + 1);
     im2col_scalar_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);

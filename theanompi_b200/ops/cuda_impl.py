@@ -186,9 +186,10 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
     M = N * Ho * Wo
     yv = y.view(M, Ot)[:, o_off:o_off + Og]
     gemm(col, w2, M, Og, K, out=yv, bias=b, bias_mode=1 if b is not None else 0, relu=relu, lda=Kp, ldb=Kp, ldc=Ot)
+    return (col, Kp, K)
 
 
-def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True):
+def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True, return_cols=False):
     x = _bf(x).contiguous()
     N, H, W, C = x.shape
     O, KH, KW, Cg = w.shape
@@ -196,24 +197,25 @@ def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True):
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
     y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=x.device)
     Og = O // groups
+    cols = []
     for g in range(groups):
-        _conv_fwd_group(x, w[g * Og:(g + 1) * Og], None if b is None else b[g * Og:(g + 1) * Og], y, g * Og, g * Cg, Cg,
-                        stride, pad, relu)
-    return y
+        cols.append(_conv_fwd_group(x, w[g * Og:(g + 1) * Og], None if b is None else b[g * Og:(g + 1) * Og], y, g * Og,
+                                    g * Cg, Cg, stride, pad, relu))
+    return (y, cols) if return_cols else y
 
 
-def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu):
+def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu, return_cols=False):
     x = _bf(x).contiguous()
     N, H, W, C = x.shape
     Og, KH, KW, Cg = w0.shape
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
     y = torch.empty((N, Ho, Wo, 2 * Og), dtype=BF16, device=x.device)
-    _conv_fwd_group(x, w0, b0, y, 0, 0, Cg, stride, pad, relu)
-    _conv_fwd_group(x, w1, b1, y, Og, Cg, Cg, stride, pad, relu)
-    return y
+    cols = [_conv_fwd_group(x, w0, b0, y, 0, 0, Cg, stride, pad, relu),
+            _conv_fwd_group(x, w1, b1, y, Og, Cg, Cg, stride, pad, relu)]
+    return (y, cols) if return_cols else y
 
 
-def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out):
+def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out, col=None):
     N, H, W, Ct = x.shape
     Og, KH, KW, _ = w.shape
     Ho, Wo, Ot = y.shape[1], y.shape[2], y.shape[3]
@@ -222,7 +224,7 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
     dyv = dy.view(M, Ot)[:, o_off:o_off + Og]
     yv = y.view(M, Ot)[:, o_off:o_off + Og]
     dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
-    col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
+    col, Kp, K = col if col is not None else _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)   # forward's matrix is reused
     dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
     # wgrad: dW[Og, K] = dymᵀ[Og, M] · col[M, K]   (both operands MN-major, split-K over M)
     gemm(dym, col, Og, K, M, a_mn=True, b_mn=True, out=dw.view(Og, K), lda=Og, ldb=Kp, ldc=K)
@@ -237,7 +239,7 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
     return dw, db
 
 
-def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None):
+def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None, cols=None):
     x = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
     N, H, W, C = x.shape
@@ -247,23 +249,26 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
     dx = torch.empty_like(x) if need_dx else None
     Og = O // groups
     if groups == 1:
-        dw, db = _conv_bwd_group(x, w, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, dw_out, db_out)
+        dw, db = _conv_bwd_group(x, w, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, dw_out, db_out,
+                                 col=cols[0] if cols else None)
         return dx, dw, db
     dw = dw_out if dw_out is not None else torch.empty(tuple(w.shape), dtype=torch.float32, device=x.device)
     db = db_out if db_out is not None else torch.empty(O, dtype=torch.float32, device=x.device)
     for g in range(groups):
         _conv_bwd_group(x, w[g * Og:(g + 1) * Og], y, dy, dx, g * Og, g * Cg, Cg, stride, pad, relu, need_dx,
-                        dw[g * Og:(g + 1) * Og], db[g * Og:(g + 1) * Og])
+                        dw[g * Og:(g + 1) * Og], db[g * Og:(g + 1) * Og], col=cols[g] if cols else None)
     return dx, dw, db
 
 
-def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, outs=(None, None, None, None)):
+def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, outs=(None, None, None, None), cols=None):
     x = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
     Og, KH, KW, Cg = w0.shape
     dx = torch.empty_like(x) if need_dx else None
-    dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1])
-    dw1, db1 = _conv_bwd_group(x, w1, y, dy, dx, Og, Cg, Cg, stride, pad, relu, need_dx, outs[2], outs[3])
+    dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1],
+                               col=cols[0] if cols else None)
+    dw1, db1 = _conv_bwd_group(x, w1, y, dy, dx, Og, Cg, Cg, stride, pad, relu, need_dx, outs[2], outs[3],
+                               col=cols[1] if cols else None)
     return dx, (dw0, db0, dw1, db1)
 
 

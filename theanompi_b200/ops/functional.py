@@ -18,7 +18,11 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import reference as ref
+
+CACHE_COL = os.environ.get("TMPI_CACHE_COL", "1") != "0"
 
 
 def _impl(x):
@@ -95,7 +99,15 @@ class _ConvFn(torch.autograd.Function):
     def forward(ctx, x, w, b, stride, pad, groups, relu):
         impl = _impl(x)
         wc = compute_weight(w)
-        y = impl.conv2d_bias_act(x, wc, b, stride, pad, groups, relu)
+        ctx.cols = None
+        if impl is ref:
+            y = ref.conv2d_bias_act(x, wc, b, stride, pad, groups, relu)
+        else:
+            # keep the im2col matrix of the forward for wgrad (memory is cheap on a 180 GB part; recomputing
+            # it cost ~13 % of the AlexNet step)
+            y, ctx.cols = impl.conv2d_bias_act(x, wc, b, stride, pad, groups, relu, return_cols=True)
+            if not CACHE_COL:
+                ctx.cols = None
         ctx.save_for_backward(x, y)
         ctx.w, ctx.b = w, b
         ctx.cfg = (stride, pad, groups, relu)
@@ -113,7 +125,8 @@ class _ConvFn(torch.autograd.Function):
             dx, dw, db = ref.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx)
         else:
             dx, dw, db = impl.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx,
-                                                  dw_out=_gout(w), db_out=_gout(b))
+                                                  dw_out=_gout(w), db_out=_gout(b), cols=ctx.cols)
+            ctx.cols = None
         gb = _sink(b, db)
         gw = _sink(w, dw)
         return dx, gw, gb, None, None, None, None
@@ -138,8 +151,11 @@ class _ConvG2Fn(torch.autograd.Function):
             y0 = ref.conv2d_bias_act(x[..., :C // 2].contiguous(), ws[0], b0, stride, pad, 1, relu)
             y1 = ref.conv2d_bias_act(x[..., C // 2:].contiguous(), ws[1], b1, stride, pad, 1, relu)
             y = torch.cat([y0, y1], dim=-1)
+            ctx.cols = None
         else:
-            y = impl.conv2d_group2_bias_act(x, ws[0], b0, ws[1], b1, stride, pad, relu)
+            y, ctx.cols = impl.conv2d_group2_bias_act(x, ws[0], b0, ws[1], b1, stride, pad, relu, return_cols=True)
+            if not CACHE_COL:
+                ctx.cols = None
         ctx.save_for_backward(x, y)
         ctx.p = (w0, b0, w1, b1)
         ctx.cfg = (stride, pad, relu)
@@ -166,7 +182,8 @@ class _ConvG2Fn(torch.autograd.Function):
         else:
             dx, grads = impl.conv2d_group2_bias_act_bwd(
                 x, compute_weight(w0), compute_weight(w1), y, dy, stride, pad, relu, need_dx,
-                outs=(_gout(w0), _gout(b0), _gout(w1), _gout(b1)))
+                outs=(_gout(w0), _gout(b0), _gout(w1), _gout(b1)), cols=ctx.cols)
+            ctx.cols = None
         gb1 = _sink(b1, grads[3])
         gw1 = _sink(w1, grads[2])
         gb0 = _sink(b0, grads[1])

@@ -186,7 +186,8 @@ class BSP_Exchanger(object):
         self.comm.Barrier()
         recorder.end("sync")
         recorder.start()
-        self.exch.exchange()
+        with torch.no_grad():
+            self.exch.exchange()
         if self.sync_type == "cdd":
             self.model.descent_vel()
         elif self.arena is not None and self.exch_strategy != "p2p32":
@@ -393,9 +394,19 @@ class GOSGD_Exchanger(object):
             self._pending_sends.append(dist.isend(self.snap, dest, group=self.group))
         self.n_pushed += 1
 
-    def finish(self):
-        """Serve inbound pushes until all of mine are acknowledged (clean shutdown)."""
+    def finish(self, count_arr=None):
+        """Clean shutdown without deadlock: (1) keep serving inbound pushes until all of mine
+        are acknowledged, (2) announce completion, (3) keep serving until every rank has
+        announced — at that point no push can be in flight any more."""
+        import time
         while self._unacked > 0:
-            self.process_messages(None)
+            self.process_messages(count_arr)
+            time.sleep(0.0005)
+        key = "%s/gosgd_done" % self.comm.prefix
+        self.comm.store.add(key, 1)
+        while int(self.comm.store.add(key, 0)) < self.size:
+            self.process_messages(count_arr)
+            time.sleep(0.0005)
+        self.process_messages(count_arr)
         for w in self._pending_sends:
             w.wait()

@@ -67,6 +67,8 @@ class Exch_allreduce(Exch_strategy):
             host = s.detach().to("cpu", torch.float32)
             if self.avg:
                 host = host / self.size
+            elif host.data_ptr() == s.data_ptr():
+                host = host.clone()                    # CPU tensors: never reduce in place into the send buffer
             host = host.contiguous()
             dist.all_reduce(host, op=dist.ReduceOp.SUM, group=self.group)
             d.copy_(host.to(d.device), non_blocking=False)

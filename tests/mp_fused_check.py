@@ -37,7 +37,7 @@ def main():
     wtypes = ["W" if len(s) > 1 else "b" for s in shapes]
     arena = FlatArena(params, wtypes, dev, weight_decay=5e-4, allocator=alloc, with_recv=True)
     gc = worker.gpucomm
-    info = dict(rank=rank, mode=gc.mode, multicast=gc.has_multicast, numel=arena.numel)
+    info = dict(rank=rank, mode=gc.mode, multicast=gc.has_multicast, multicast_error=gc.multicast_error, numel=arena.numel)
     L = native.require()
     results = {}
 

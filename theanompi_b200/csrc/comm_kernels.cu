@@ -184,6 +184,9 @@ __device__ __forceinline__ float4 gather_grad(const FusedArgs& a, long long i) {
 }
 
 // ---- one-shot: every rank reduces every block itself
+// U arena blocks are in flight per CTA iteration (U x world independent 16 B peer loads per thread) — a single
+// load per thread cannot cover the ~2 us NVLink round trip.
+template <int U>
 __global__ void __launch_bounds__(kThreads) fused_oneshot_sgd_kernel(const FusedArgs a) {
   const Hyper h{*a.lr_ptr, a.mu, a.inv_k, a.nesterov};
   const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
@@ -193,22 +196,34 @@ __global__ void __launch_bounds__(kThreads) fused_oneshot_sgd_kernel(const Fused
   }
   block_barrier(a.ctx);                                  // peers' gradients (or wire copies) are complete
   float* W = region<float>(a.ctx, a.ctx.rank, a.w_off);
-  float* U = region<float>(a.ctx, a.ctx.rank, a.u_off);
-  for (long long b = blo + blockIdx.x; b < bhi; b += gridDim.x) {
-    const int g = a.block_group[b];
-    if (!a.tab.exch[g]) { local_block_update(a, h, b, g); continue; }
-    const long long i = b * kArenaBlock + threadIdx.x * 4;
-    const float4 gs = gather_grad(a, i);
-    float4 w = *reinterpret_cast<const float4*>(W + i), u = *reinterpret_cast<const float4*>(U + i);
-    sgd4(w, u, gs, h, a.tab.lr_mult[g], a.tab.wd[g]);
-    *reinterpret_cast<float4*>(W + i) = w;
-    *reinterpret_cast<float4*>(U + i) = u;
-    if (a.h_off >= 0) *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.h_off) + i) = pack_bf16x4(w);
+  float* U_ = region<float>(a.ctx, a.ctx.rank, a.u_off);
+  for (long long b0 = blo + blockIdx.x; b0 < bhi; b0 += (long long)gridDim.x * U) {
+    float4 gs[U]; int grp[U]; bool ex[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      ex[u] = false; grp[u] = -1;
+      if (b < bhi) { grp[u] = a.block_group[b]; ex[u] = a.tab.exch[grp[u]] != 0; }
+      if (ex[u]) gs[u] = gather_grad(a, b * kArenaBlock + threadIdx.x * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      if (grp[u] < 0) continue;
+      if (!ex[u]) { local_block_update(a, h, b, grp[u]); continue; }
+      const long long i = b * kArenaBlock + threadIdx.x * 4;
+      float4 w = *reinterpret_cast<const float4*>(W + i), uu = *reinterpret_cast<const float4*>(U_ + i);
+      sgd4(w, uu, gs[u], h, a.tab.lr_mult[grp[u]], a.tab.wd[grp[u]]);
+      *reinterpret_cast<float4*>(W + i) = w;
+      *reinterpret_cast<float4*>(U_ + i) = uu;
+      if (a.h_off >= 0) *reinterpret_cast<uint2*>(region<__nv_bfloat16>(a.ctx, a.ctx.rank, a.h_off) + i) = pack_bf16x4(w);
+    }
   }
   block_barrier(a.ctx);                                  // nobody overwrites G while a peer still reads it
 }
 
 // ---- two-shot: rank r owns a contiguous slice of the range; reduce → update → push W (+H) to every peer
+template <int U>
 __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const FusedArgs a, int use_nvls) {
   const Hyper h{*a.lr_ptr, a.mu, a.inv_k, a.nesterov};
   const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
@@ -226,31 +241,43 @@ __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const Fused
   block_barrier(a.ctx);
   const long long s0 = blo + R * per, s1 = min(bhi, s0 + per);
   float* W = region<float>(a.ctx, R, a.w_off);
-  float* U = region<float>(a.ctx, R, a.u_off);
-  for (long long b = s0 + blockIdx.x; b < s1; b += gridDim.x) {
-    const int g = a.block_group[b];
-    if (!a.tab.exch[g]) continue;
-    const long long i = b * kArenaBlock + threadIdx.x * 4;
-    float4 gs;
-    if (use_nvls) {
-      gs = a.wire16 ? unpack_bf16x4(mc_ld_reduce_bf16x4(reinterpret_cast<char*>(a.ctx.mc_arena) + a.wire_off + i * 2))
-                    : mc_ld_reduce_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.g_off) + i);
-    } else {
-      gs = gather_grad(a, i);
-    }
-    float4 w = *reinterpret_cast<const float4*>(W + i), u = *reinterpret_cast<const float4*>(U + i);
-    sgd4(w, u, gs, h, a.tab.lr_mult[g], a.tab.wd[g]);
-    *reinterpret_cast<float4*>(U + i) = u;
-    const uint2 wh = pack_bf16x4(w);
-    if (use_nvls) {
-      mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
-      if (a.h_off >= 0) mc_st_u2(reinterpret_cast<char*>(a.ctx.mc_arena) + a.h_off + i * 2, wh);
-    } else {
+  float* U_ = region<float>(a.ctx, R, a.u_off);
+  for (long long b0 = s0 + blockIdx.x; b0 < s1; b0 += (long long)gridDim.x * U) {
+    float4 gs[U]; int grp[U];
 #pragma unroll
-      for (int p = 0; p < kMaxRanks; ++p) {
-        if (p < Wn) {
-          st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
-          if (a.h_off >= 0) st_u2(region<__nv_bfloat16>(a.ctx, p, a.h_off) + i, wh);
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      grp[u] = -1;
+      if (b < s1) { const int g = a.block_group[b]; if (a.tab.exch[g]) grp[u] = g; }
+      if (grp[u] >= 0) {
+        const long long i = b * kArenaBlock + threadIdx.x * 4;
+        if (use_nvls) {
+          gs[u] = a.wire16 ? unpack_bf16x4(mc_ld_reduce_bf16x4(reinterpret_cast<char*>(a.ctx.mc_arena) + a.wire_off + i * 2))
+                           : mc_ld_reduce_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.g_off) + i);
+        } else {
+          gs[u] = gather_grad(a, i);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (grp[u] < 0) continue;
+      const long long b = b0 + (long long)u * gridDim.x;
+      const long long i = b * kArenaBlock + threadIdx.x * 4;
+      float4 w = *reinterpret_cast<const float4*>(W + i), uu = *reinterpret_cast<const float4*>(U_ + i);
+      sgd4(w, uu, gs[u], h, a.tab.lr_mult[grp[u]], a.tab.wd[grp[u]]);
+      *reinterpret_cast<float4*>(U_ + i) = uu;
+      const uint2 wh = pack_bf16x4(w);
+      if (use_nvls) {
+        mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
+        if (a.h_off >= 0) mc_st_u2(reinterpret_cast<char*>(a.ctx.mc_arena) + a.h_off + i * 2, wh);
+      } else {
+#pragma unroll
+        for (int p = 0; p < kMaxRanks; ++p) {
+          if (p < Wn) {
+            st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
+            if (a.h_off >= 0) st_u2(region<__nv_bfloat16>(a.ctx, p, a.h_off) + i, wh);
+          }
         }
       }
     }
@@ -276,11 +303,15 @@ void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStrea
   const long long nb = (a.hi - a.lo) / kArenaBlock;
   if (nb <= 0) return;
   if (algo == 2 && a.ctx.mc_arena == nullptr) throw std::runtime_error("fused_allreduce_sgd: NVLS requested without a multicast mapping");
+  const bool wide = a.ctx.world > 4;                     // keep (U x world) peer loads per thread around 8..16
   if (algo == 0) {
-    fused_oneshot_sgd_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
+    if (wide) fused_oneshot_sgd_kernel<2><<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
+    else fused_oneshot_sgd_kernel<4><<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
   } else {
     const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
-    fused_twoshot_sgd_kernel<<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, algo == 2 ? 1 : 0);
+    const int nv = algo == 2 ? 1 : 0;
+    if (wide && !nv) fused_twoshot_sgd_kernel<2><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
+    else fused_twoshot_sgd_kernel<4><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
   }
   count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd"); ::tmpi::check_capture(st, "fused_allreduce_sgd");
 }

@@ -133,7 +133,14 @@ PeerArena::PeerArena(int rank, int world, int device, size_t arena_bytes, const 
       size_t gran = 0;
       drv::check(drv::p_cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED), "cuMemGetAllocationGranularity");
       gran_ = gran;
-      arena_bytes_ = round_up(arena_bytes, gran);
+      if (world > 1) {
+        // the multicast object (NVLS) wants the bound range to be a multiple of ITS granularity as well
+        CUmulticastObjectProp mp; memset(&mp, 0, sizeof(mp));
+        mp.numDevices = (unsigned)world; mp.size = round_up(arena_bytes, gran); mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        size_t mg = 0;
+        if (drv::p_cuMulticastGetGranularity(&mg, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mg > gran_) gran_ = mg;
+      }
+      arena_bytes_ = round_up(arena_bytes, gran_);
       sig_bytes_ = round_up(sig_bytes_, gran);
       drv::check(drv::p_cuMemCreate(&impl_->h_arena, arena_bytes_, &prop, 0), "cuMemCreate(arena)");
       drv::check(drv::p_cuMemCreate(&impl_->h_sig, sig_bytes_, &prop, 0), "cuMemCreate(signal pad)");

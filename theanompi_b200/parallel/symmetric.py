@@ -47,6 +47,7 @@ class SymmetricComm(object):
             raise RuntimeError("symmetric peer memory spans one node; use exch_strategy nccl32 across nodes")
         self.pa = None
         self.has_multicast = False
+        self.multicast_error = None
         self.nbytes = 0
         self.max_blocks = int(os.environ.get("TMPI_COMM_BLOCKS", "0")) or None
         self._tensors = {}
@@ -99,9 +100,11 @@ class SymmetricComm(object):
                 self.pa.mc_create_and_send()
         except Exception as e:  # noqa: BLE001
             err = repr(e)
-        if any(self.comm.allgather(err)):
+        errs = self.comm.allgather(err)
+        if any(errs):
+            self.multicast_error = "create: %s" % [e for e in errs if e]
             if self.comm.rank == 0:
-                print("[symmetric] NVLS multicast unavailable (create):", [e for e in self.comm.allgather(err) if e])
+                print("[symmetric] NVLS multicast unavailable (%s)" % self.multicast_error)
             return
         steps = [self.pa.mc_recv, self.pa.mc_add_device, self.pa.mc_bind_and_map]
         for fn in steps:
@@ -112,8 +115,9 @@ class SymmetricComm(object):
                 err = repr(e)
             errs = self.comm.allgather(err)
             if any(errs):
+                self.multicast_error = "%s: %s" % (fn.__name__, [e for e in errs if e])
                 if self.comm.rank == 0:
-                    print("[symmetric] NVLS multicast unavailable (%s): %s" % (fn.__name__, [e for e in errs if e]))
+                    print("[symmetric] NVLS multicast unavailable (%s)" % self.multicast_error)
                 return
         self.has_multicast = True
 

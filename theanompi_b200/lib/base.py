@@ -1,0 +1,1 @@
+from ..parallel.base import *  # noqa: F401,F403

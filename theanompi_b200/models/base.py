@@ -109,7 +109,8 @@ class ModelBase(object):
         count_params(self.params, verbose=False)
         allocator = self.config.get("arena_allocator")
         self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta,
-                               with_recv=allocator is not None, allocator=allocator)
+                               with_recv=allocator is not None, allocator=allocator,
+                               shadow=self.config.get("_arena_shadow"))
         self.shared_lr = SharedScalar(self.arena.hyper, 0, self.base_lr)
         self.sgd = FlatSGD(self.arena, self.mu, self.use_nesterov_momentum, self.use_momentum)
         B = self.batch_size

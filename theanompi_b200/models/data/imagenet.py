@@ -143,6 +143,20 @@ class ImageNet_data(object):
             if self.verbose:
                 print("validation data sharded", self.n_batch_val)
 
+    def load_batch(self, item, mode, model):
+        """Serial (no loader) path of the reference (``alex_net.py:420-438``): read, normalise,
+        crop/mirror on the host, return an NHWC float tensor."""
+        import torch
+        from .utils import crop_and_mirror
+        raw = np.empty((self.file_batch_size, self.height, self.width, self.channels), dtype=np.uint8)
+        self.read(item, raw)
+        arr = (raw.astype(np.float32) - self.rawdata[4]) / 255.0
+        arr = crop_and_mirror(arr, mode, model.rand_crop, model.batch_crop_mirror, model.input_width)
+        t = torch.from_numpy(arr)
+        if model.cuda:
+            t = t.pin_memory().to(model.device, non_blocking=True)
+        return t
+
     # ------------------------------------------------------------------ parallel loading
     def spawn_load(self):
         """The reference spawns an MPI child here (``:226-267``); the B200 loader is a

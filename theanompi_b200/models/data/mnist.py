@@ -56,7 +56,9 @@ class MNIST_data(object):
         B = self.batch_size
         while True:
             idx = rs.permutation(len(x)) if shuffle else np.arange(len(x))
-            for s in range(0, len(x) - B + 1, B):
+            if len(idx) < B:                        # tiny (synthetic / test) sets: tile up to one batch
+                idx = np.resize(idx, B)
+            for s in range(0, len(idx) - B + 1, B):
                 sel = idx[s:s + B]
                 yield x[sel], y[sel]
             if not forever:

@@ -5,7 +5,7 @@ N=${1:-2}
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 tests/mp_fused_check.py --sweep > gpurun_out/mp_fused_full_$N.log 2>&1
 grep -n -A25 "Traceback" gpurun_out/mp_fused_full_$N.log | head -60
 grep -E "symmetric|MP_FUSED" gpurun_out/mp_fused_full_$N.log | cut -c1-1500
-for cfg in "fused" "fused --no-overlap" "twoshot --no-overlap" "fused16" "nccl32"; do
+IFS=";" read -ra CFGS <<< "${BENCH_CFGS:-fused;fused --no-overlap;nccl32}"; for cfg in "${CFGS[@]}"; do
   set -- $cfg; s=$1; shift
   echo "=== bench N=$N strategy=$s $*"
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29612 bench.py --gpus $N --steps 40 --warmup 5 --strategy $s $* > gpurun_out/bench${N}_${s}_$#.log 2>&1

@@ -31,12 +31,16 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;
 
 template <int BN> struct Cfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : (BN == 64 ? 4 : 5);   // <= ~100 KB: two CTAs co-reside per SM
+  // persistent kernel, one CTA per SM: operand ring + a dedicated epilogue staging tile + 2 TMEM accumulators
+  static constexpr int STAGES = (BN == 128) ? 4 : (BN == 64 ? 6 : 8);
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = (BN < 32) ? 32 : BN;   // power of two >= 32
+  static constexpr int STAGING_PITCH_MAX = BN * 4 + 16;                 // fp32 row + 16 B (conflict-free v4 stores)
+  static constexpr int STAGING_BYTES = BM * STAGING_PITCH_MAX;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int ACC_STAGES = 2;
+  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;         // power of two >= 32 (64 / 128 / 256)
 };
 
 struct Params {
@@ -49,7 +53,8 @@ struct Params {
   int out_bf16;         // 1 = bf16 output, 0 = fp32
   int bias_mode;        // 0 none, 1 per-column (N), 2 per-row (M)
   int relu;
-  int kb_per_split;     // k-blocks per grid.z slice
+  int kb_per_split;     // k-blocks per split-K slice
+  int mt, nt, splits;   // tile grid (the kernel is persistent: tiles are walked round-robin by the CTAs)
   int atomic_out;       // 1 = fp32 atomicAdd (split-K)
 };
 
@@ -61,6 +66,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -135,32 +143,37 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // ------------------------------------------------------------------ the kernel
+// Persistent: grid = min(#tiles, #SMs); CTA c processes tiles c, c+grid, … .  Three pipelines run concurrently:
+//   TMA warp  → smem ring (full/empty mbarriers)           → MMA thread
+//   MMA thread → TMEM accumulator A/B (tmem_full/tmem_empty) → epilogue warps
+// so the epilogue of tile i overlaps the main loop of tile i+1 and all per-CTA setup (TMEM alloc, barrier init,
+// descriptor fetch) is paid once per SM instead of once per tile.
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024B alignment
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = staging_base + C::STAGING_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
-  const uint32_t tmem_full_bar = bar_base + 8u * (2 * C::STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 1);
+  auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + C::ACC_STAGES + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 2 * C::ACC_STAGES);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
   const int num_kb_total = (p.K + BK - 1) / BK;
-  const int kb0 = blockIdx.z * p.kb_per_split;
-  const int kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+  const int tiles_mn = p.mt * p.nt;
+  const int total_tiles = tiles_mn * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -168,32 +181,37 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_acc = *tmem_slot_ptr;
+  const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-        const uint32_t sb = sa + C::A_BYTES;
-        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-        if (!p.a_mn) {
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
-        } else {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn, rem = tile % tiles_mn;
+        const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
+          } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
-            tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
-        }
-        if (!p.b_mn) {
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
-        } else {
+            for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-            tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
     __syncwarp();
@@ -209,115 +227,135 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_sbo = 1024u, a_step = p.a_mn ? 128u : 2u;
       const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_sbo = 1024u, b_step = p.b_mn ? 128u : 2u;
       int stage = 0; uint32_t phase = 0;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      int t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        const int acc = t & 1;
+        mbar_wait(tmem_empty_bar(acc), (uint32_t)(((t >> 1) & 1) ^ 1));       // epilogue drained this accumulator
         tc_fence_after();
-        const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-        const uint32_t sb = sa + C::A_BYTES;
-        const uint64_t adesc0 = make_smem_desc(sa, a_lbo, a_sbo);
-        const uint64_t bdesc0 = make_smem_desc(sb, b_lbo, b_sbo);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc0 = make_smem_desc(sa, a_lbo, a_sbo);
+          const uint64_t bdesc0 = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc,
-                    (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));             // frees the smem slot once these MMAs retire
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));             // frees the smem slot once these MMAs retire
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        umma_commit(tmem_full_bar(acc));             // accumulator complete → epilogue
       }
-      umma_commit(tmem_full_bar);                  // accumulator complete → epilogue
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM → registers → (smem staging) → global =====================
+    // ===================== epilogue: TMEM → registers → smem staging → global =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int row = 32 * q + lane;                 // row inside the tile
-    const int m = m0 + row;
-    const bool m_ok = m < p.M;
-    float bias_m = 0.f;
-    if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
-    // Fast path: the whole tile is in range and 16-byte aligned → stage it through the (now idle) operand smem so
-    // global stores are full coalesced 16 B vectors along the row instead of one strided row chunk per lane.
     const int esz = p.out_bf16 ? 2 : 4;
-    const bool staged = !p.atomic_out && (n0 + BN <= p.N) && (((long long)p.ldc * esz) % 16 == 0) &&
-                        ((reinterpret_cast<uintptr_t>(p.C) + (long long)n0 * esz) % 16 == 0);
-    const uint32_t pitch = (uint32_t)(BN * esz + 16);                      // +16 B: conflict-free v4 stores
-    uint8_t* stage_ptr = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t pitch = (uint32_t)(BN * esz + 16);
+    uint8_t* stage_ptr = smem_raw + (staging_base - smem_u32(smem_raw));
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int rem = tile % tiles_mn;
+      const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
+      const int acc = t & 1;
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      mbar_wait(tmem_full_bar(acc), (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool m_ok = m < p.M;
+      float bias_m = 0.f;
+      if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
+      // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores.
+      const bool staged = !p.atomic_out && (n0 + BN <= p.N) && (((long long)p.ldc * esz) % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.C) + (long long)n0 * esz) % 16 == 0);
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
-      tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
-      tmem_ld_wait();
-      const int nb = n0 + 32 * c;
-      if (!staged && (!m_ok || nb >= p.N)) continue;
-      float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
+        tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+        tmem_ld_wait();
+        if (c == BN / 32 - 1) {
+          // all of this warp's TMEM reads for the tile are done → hand the accumulator back to the MMA thread
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        const int nb = n0 + 32 * c;
+        if (!staged && (!m_ok || nb >= p.N)) continue;
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]) * p.alpha;
-        if (p.bias_mode == 1) { x += (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f; }
-        else if (p.bias_mode == 2) { x += bias_m; }
-        if (p.relu) x = fmaxf(x, 0.f);
-        v[j] = x;
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]) * p.alpha;
+          if (p.bias_mode == 1) { x += (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f; }
+          else if (p.bias_mode == 2) { x += bias_m; }
+          if (p.relu) x = fmaxf(x, 0.f);
+          v[j] = x;
+        }
+        if (staged) {
+          uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)(32 * c) * esz;
+          if (p.out_bf16) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+          continue;
+        }
+        const bool full = (nb + 32 <= p.N);
+        if (p.atomic_out) {
+          float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (full || nb + j < p.N) atomicAdd(dst + j, v[j]);
+        } else if (p.out_bf16) {
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f_to_bf16(v[j]);
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+          }
+        }
       }
       if (staged) {
-        uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)(32 * c) * esz;
-        if (p.out_bf16) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        continue;
-      }
-      const bool full = (nb + 32 <= p.N);
-      if (p.atomic_out) {
-        float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) if (full || nb + j < p.N) atomicAdd(dst + j, v[j]);
-      } else if (p.out_bf16) {
-        __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f_to_bf16(v[j]);
-        }
-      } else {
-        float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
-        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
-        }
-      }
-    }
-    if (staged) {
-      // each warp re-reads only the 32 rows it staged itself → a warp-level sync is enough
-      __syncwarp();
-      const int vec_per_row = (BN * esz) / 16;                 // 16-byte vectors per tile row
-      const int rows_per_it = 32 / vec_per_row > 0 ? 32 / vec_per_row : 1;
-      uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)n0 * esz;
-      if (vec_per_row <= 32) {
+        // each warp re-reads only the 32 rows it staged itself → a warp-level sync is enough
+        __syncwarp();
+        const int vec_per_row = (BN * esz) / 16;                 // 16-byte vectors per tile row (<= 32)
+        const int rows_per_it = 32 / vec_per_row;
+        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)n0 * esz;
         const int lr = lane / vec_per_row, lv = lane % vec_per_row;
         for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
           const int rr = 32 * q + r0 + lr;
-          if (lr < rows_per_it && m0 + rr < p.M) {
+          if (m0 + rr < p.M) {
             const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + (size_t)rr * pitch + (size_t)lv * 16);
             *reinterpret_cast<uint4*>(gbase + (long long)(m0 + rr) * p.ldc * esz + (long long)lv * 16) = val;
           }
         }
+        __syncwarp();                                            // staging rows are free for the next tile
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_acc, C::TMEM_COLS); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------ host side
@@ -365,14 +403,15 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
 }
 
 template <int BN>
-static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, int splits, cudaStream_t st) {
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st) {
   using C = Cfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
     check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
     attr_set = true;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, splits);
+  const long long total = (long long)p.mt * p.nt * splits;
+  const int grid = (int)std::min<long long>(total, (long long)sm_count());
   gemm_bf16_tcgen05<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   count_launch();
   TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
@@ -414,6 +453,7 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   Params p;
   p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
+  p.mt = mt; p.nt = nt; p.splits = splits;
   if (splits > 1) {
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
     check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");

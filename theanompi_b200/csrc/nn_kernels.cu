@@ -484,26 +484,36 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
 struct ConvGeom { int N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p; long long ldcol; int K; };
 
 // col[m, (kh*KW+kw)*Cg + c] = x[n, ho*s-p+kh, wo*s-p+kw, c_off+c]   (zero outside the image)
-__global__ void im2col_vec8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
+__global__ void __launch_bounds__(256) im2col_vec8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ col, ConvGeom g) {
+  // one CTA per IM2COL_ROWS consecutive output pixels; (n, ho, wo) is decoded once per row, the threads sweep the
+  // row's KH*KW*(Cg/8) 16-byte vectors with 32-bit index math only.
+  constexpr int IM2COL_ROWS = 8;
   const int cvn = g.Cg >> 3;
   const int per_m = g.KH * g.KW * cvn;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long M = (long long)g.N * g.Ho * g.Wo;
-  if (idx >= M * per_m) return;
-  const long long m = idx / per_m; int rem = (int)(idx % per_m);
-  const int kk = rem / cvn, cv = rem % cvn;
-  const int kh = kk / g.KW, kw = kk % g.KW;
-  const int wo = (int)(m % g.Wo); long long t = m / g.Wo;
-  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
-  const int h = ho * g.s - g.p + kh, w = wo * g.s - g.p + kw;
-  bf16x8 v;
-  if (h >= 0 && h < g.H && w >= 0 && w < g.W)
-    v = *reinterpret_cast<const bf16x8*>(x + (((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off + cv * 8);
-  else {
+  const long long M = (long long)g.N * g.Ho * g.Wo;
+  const long long m_base = (long long)blockIdx.x * IM2COL_ROWS;
+  for (int rr = 0; rr < IM2COL_ROWS; ++rr) {
+    const long long m = m_base + rr;
+    if (m >= M) return;
+    const int wo = (int)(m % g.Wo); const long long t = m / g.Wo;
+    const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
+    const int h0 = ho * g.s - g.p, w0 = wo * g.s - g.p;
+    const __nv_bfloat16* xin = x + (long long)n * g.H * g.W * g.Ctot + g.c_off;
+    __nv_bfloat16* dst = col + m * g.ldcol;
+    for (int v = threadIdx.x; v < per_m; v += blockDim.x) {
+      const int kk = v / cvn, cv = v - kk * cvn;
+      const int kh = kk / g.KW, kw = kk - kh * g.KW;
+      const int h = h0 + kh, w = w0 + kw;
+      bf16x8 val;
+      if (h >= 0 && h < g.H && w >= 0 && w < g.W)
+        val = *reinterpret_cast<const bf16x8*>(xin + ((long long)h * g.W + w) * g.Ctot + cv * 8);
+      else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+        for (int i = 0; i < 4; ++i) val.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+      }
+      *reinterpret_cast<bf16x8*>(dst + kk * g.Cg + cv * 8) = val;
+    }
   }
-  *reinterpret_cast<bf16x8*>(col + m * g.ldcol + (long long)kk * g.Cg + cv * 8) = v;
 }
 
 // generic (any Cg): one thread per (m, kh*KW+kw); the extra index KH*KW zero-fills the K..ldcol padding
@@ -532,34 +542,38 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const __nv_bfloat16* _
   extern __shared__ __nv_bfloat16 rows[];                  // [KH][W*Cg]
   const int n = blockIdx.x / g.Ho, ho = blockIdx.x % g.Ho;
   const int rowlen = g.W * g.Cg;
-  for (int i = threadIdx.x; i < g.KH * rowlen; i += blockDim.x) {
-    const int kh = i / rowlen, e = i % rowlen;
+  const bool dense = (g.Cg == g.Ctot);                     // all channels used: an input row is one contiguous span
+  for (int kh = 0; kh < g.KH; ++kh) {
     const int h = ho * g.s - g.p + kh;
-    __nv_bfloat16 v = f_to_bf16(0.f);
-    if (h >= 0 && h < g.H) {
-      const int w = e / g.Cg, c = e % g.Cg;
-      v = x[(((long long)n * g.H + h) * g.W + w) * g.Ctot + g.c_off + c];
+    __nv_bfloat16* dst = rows + kh * rowlen;
+    if (h < 0 || h >= g.H) {
+      for (int e = threadIdx.x; e < rowlen; e += blockDim.x) dst[e] = f_to_bf16(0.f);
+    } else if (dense) {
+      const __nv_bfloat16* src = x + ((long long)n * g.H + h) * g.W * g.Ctot;
+      for (int e = threadIdx.x; e < rowlen; e += blockDim.x) dst[e] = src[e];
+    } else {
+      const __nv_bfloat16* src = x + ((long long)n * g.H + h) * g.W * g.Ctot + g.c_off;
+      for (int e = threadIdx.x; e < rowlen; e += blockDim.x) { const int w = e / g.Cg; dst[e] = src[(long long)w * g.Ctot + (e - w * g.Cg)]; }
     }
-    rows[i] = v;
   }
   __syncthreads();
   const int run = g.KW * g.Cg;                             // contiguous elements per (kh)
   const int vec_per_row = (int)(g.ldcol >> 3);
   __nv_bfloat16* out = col + ((long long)n * g.Ho + ho) * g.Wo * g.ldcol;
   for (int i = threadIdx.x; i < g.Wo * vec_per_row; i += blockDim.x) {
-    const int wo = i / vec_per_row, e0 = (i % vec_per_row) * 8;
+    const int wo = i / vec_per_row, e0 = (i - wo * vec_per_row) * 8;
     const int xbase = (wo * g.s - g.p) * g.Cg;              // may be negative with padding
+    int kh = e0 / run, r = e0 - kh * run;
     __align__(16) __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int e = e0 + j;
       __nv_bfloat16 t = f_to_bf16(0.f);
-      if (e < g.K) {
-        const int kh = e / run, r = e % run;
+      if (e0 + j < g.K) {
         const int xi = xbase + r;
         if (xi >= 0 && xi < rowlen) t = rows[kh * rowlen + xi];
       }
       v[j] = t;
+      if (++r == run) { r = 0; ++kh; }
     }
     *reinterpret_cast<uint4*>(out + (long long)wo * g.ldcol + e0) = *reinterpret_cast<const uint4*>(v);
   }
@@ -567,11 +581,11 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const __nv_bfloat16* _
 
 // dx[n,h,w,c_off+c] = sum over (kh,kw) with (h+p-kh)%s==0, (w+p-kw)%s==0 of dcol[m(n,ho,wo), (kh*KW+kw)*Cg + c]
 __global__ void col2im_vec8_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dx, ConvGeom g) {
-  const int cvn = g.Cg >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)g.N * g.H * g.W * cvn;
+  const unsigned cvn = (unsigned)(g.Cg >> 3);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;           // host guarantees total < 2^32
+  const unsigned total = (unsigned)g.N * g.H * g.W * cvn;
   if (idx >= total) return;
-  const int cv = (int)(idx % cvn); long long t = idx / cvn;
+  const int cv = (int)(idx % cvn); unsigned t = idx / cvn;
   const int w = (int)(t % g.W); t /= g.W;
   const int h = (int)(t % g.H); const int n = (int)(t / g.H);
   float acc[8];
@@ -602,8 +616,7 @@ void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, 
   ConvGeom g{N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, KH * KW * Cg};
   long long M = (long long)N * Ho * Wo;
   if (Cg % 8 == 0 && c_off % 8 == 0 && Ctot % 8 == 0 && ldcol % 8 == 0) {
-    long long total = M * KH * KW * (Cg / 8);
-    im2col_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
+    im2col_vec8_kernel<<<grid_for(M, 8), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
   } else if (ldcol % 8 == 0 && (size_t)KH * W * Cg * 2 <= 48 * 1024) {
     im2col_rows_kernel<<<N * Ho, 256, (size_t)KH * W * Cg * 2, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)col, g);
   } else {
@@ -618,6 +631,7 @@ void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off
   if (Cg % 8 || c_off % 8 || Ctot % 8 || ldcol % 8) throw std::runtime_error("col2im: channel counts must be multiples of 8");
   ConvGeom g{N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, KH * KW * Cg};
   long long total = (long long)N * H * W * (Cg / 8);
+  if (total >= (1LL << 32)) throw std::runtime_error("col2im: tensor too large for 32-bit indexing");
   col2im_vec8_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dcol, (__nv_bfloat16*)dx, g);
   count_launch(); TMPI_CHECK_LAUNCH("col2im"); ::tmpi::check_capture(st, "col2im");
 }

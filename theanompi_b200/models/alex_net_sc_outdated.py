@@ -29,10 +29,10 @@ class AlexNet_sc(AlexNet):
         import numpy as np
         import torch
         raw = np.empty((self.file_batch_size, self.data.height, self.data.width, self.channels), dtype=np.uint8)
-        self.data.read(img[idx], raw)
-        t = torch.from_numpy(raw)
+        src = self.data.read(img[idx], raw)
+        t = src if src is not None else torch.from_numpy(raw)
         if self.cuda:
-            t = t.pin_memory().to(self.device, non_blocking=True)
+            t = (t if t.is_pinned() else t.pin_memory()).to(self.device, non_blocking=True)
         self.shared_x.copy_(t.to(self.act_dtype) / 255.0)
         self._labels_to_device(labels[idx])
         return idx == n_batches - 1

@@ -78,11 +78,20 @@ class ImageNet_data(object):
     def read(self, filename, out):
         """Fill ``out`` (uint8 NHWC numpy view of a pinned buffer) with one file batch."""
         if filename.startswith("synthetic://"):
+            import torch
             if self._pool is None:
                 rs = np.random.RandomState(self._seed)
-                self._pool = [rs.randint(0, 256, out.shape, dtype=np.uint8) for _ in range(self._pool_n)]
+                pin = torch.cuda.is_available()
+                self._pool = []
+                for _ in range(self._pool_n):                      # synthetic "files" live in pinned memory
+                    t = torch.empty(tuple(out.shape), dtype=torch.uint8, pin_memory=pin)
+                    t.numpy()[...] = rs.randint(0, 256, out.shape, dtype=np.uint8)
+                    self._pool.append(t)
             idx = int(filename.rsplit("/", 1)[1])
-            np.copyto(out, self._pool[idx % self._pool_n])
+            src = self._pool[idx % self._pool_n]
+            if getattr(self, "zero_copy", True):
+                return src                                          # the loader DMAs straight from this buffer
+            np.copyto(out, src.numpy())
         else:
             arr = np.load(filename, mmap_mode="r")
             np.copyto(out, arr)
@@ -149,7 +158,9 @@ class ImageNet_data(object):
         import torch
         from .utils import crop_and_mirror
         raw = np.empty((self.file_batch_size, self.height, self.width, self.channels), dtype=np.uint8)
-        self.read(item, raw)
+        src = self.read(item, raw)
+        if src is not None:
+            raw = src.numpy()
         arr = (raw.astype(np.float32) - self.rawdata[4]) / 255.0
         arr = crop_and_mirror(arr, mode, model.rand_crop, model.batch_crop_mirror, model.input_width)
         t = torch.from_numpy(arr)

@@ -90,13 +90,16 @@ class ParaLoader(object):
         N, H, W, C = self.raw_shape
         if self.cuda and self.consumed[s] is not None:
             self.consumed[s].synchronize()          # trainer finished reading slot s
-        self.read_fn(item, self.host[s].numpy())
+        src = self.read_fn(item, self.host[s].numpy())          # may return its own pinned uint8 tensor (zero host copy)
+        if not (isinstance(src, torch.Tensor) and src.dtype == torch.uint8 and tuple(src.shape) == self.raw_shape
+                and (not self.cuda or src.is_pinned())):
+            src = self.host[s]
         offs, flips = draw_crops(N, (H, W), self.crop_hw, mode, self.rand_crop, self.batch_crop_mirror, self.rs)
         self.host_offs[s].numpy()[...] = offs
         self.host_flip[s].numpy()[...] = flips
         if self.cuda:
             with torch.cuda.stream(self.copy_stream):
-                self.stage[s].copy_(self.host[s], non_blocking=True)
+                self.stage[s].copy_(src, non_blocking=True)
                 self.dev_offs[s].copy_(self.host_offs[s], non_blocking=True)
                 self.dev_flip[s].copy_(self.host_flip[s], non_blocking=True)
                 from ...ops import cuda_impl
@@ -106,7 +109,7 @@ class ParaLoader(object):
                 ready = torch.cuda.Event()
                 ready.record(self.copy_stream)
         else:
-            x = ops.reference.crop_mirror_normalize(self.host[s], self.mean, self.std_scale, self.crop_hw,
+            x = ops.reference.crop_mirror_normalize(src, self.mean, self.std_scale, self.crop_hw,
                                                     self.host_offs[s], self.host_flip[s], self.out_dtype)
             self.out[s].copy_(x)
             ready = None

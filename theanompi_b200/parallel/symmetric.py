@@ -165,8 +165,11 @@ class SymmetricComm(object):
             if algo == "nvls" and not self.has_multicast:
                 return ALGO["twoshot"]
             return ALGO[algo]
-        thresh = int(os.environ.get("TMPI_ONESHOT_BYTES", str(512 * 1024)))
-        if nbytes <= thresh or self.size == 2 and nbytes <= 4 * thresh:
+        # measured crossovers (profiles/allreduce_sweep.md): 8 ranks — two-shot/NVLS wins from 16 KiB up;
+        # 2 ranks — one-shot is on par up to a few MiB (a single barrier pair, no push phase)
+        default = 2 << 20 if self.size == 2 else (64 << 10 if self.size <= 4 else 8 << 10)
+        thresh = int(os.environ.get("TMPI_ONESHOT_BYTES", str(default)))
+        if nbytes <= thresh:
             return ALGO["oneshot"]
         return ALGO["nvls"] if self.has_multicast else ALGO["twoshot"]
 

@@ -89,7 +89,12 @@ def test_linear_fwd_bwd():
     dict(N=4, H=31, W=31, C=3, O=32, k=11, s=4, p=0),      # conv1-like (C=3, K % 8 != 0)
     dict(N=3, H=13, W=13, C=64, O=96, k=3, s=1, p=1),
     dict(N=2, H=14, W=14, C=32, O=48, k=5, s=1, p=2),
-    dict(N=2, H=12, W=12, C=64, O=32, k=1, s=1, p=0),      # 1x1 fast path
+    dict(N=2, H=12, W=12, C=64, O=32, k=1, s=1, p=0),      # 1x1
+    dict(N=2, H=16, W=16, C=64, O=128, k=3, s=2, p=1),     # strided: implicit fprop/wgrad, explicit dgrad
+    dict(N=2, H=9, W=9, C=16, O=24, k=1, s=1, p=0),        # C < 64: TMA zero-fills the channel tail
+    dict(N=2, H=12, W=12, C=192, O=64, k=3, s=1, p=1),     # 3 channel chunks per tap
+    dict(N=3, H=27, W=27, C=48, O=128, k=5, s=1, p=2),     # AlexNet conv2 group shape (C = 48)
+    dict(N=40, H=13, W=13, C=256, O=384, k=3, s=1, p=1),   # many tiles + split-K wgrad
 ])
 def test_conv_fwd_bwd(cfg):
     torch.manual_seed(4)
@@ -115,9 +120,10 @@ def test_conv_fwd_bwd(cfg):
         assert rel_err(x.grad, dxr) < 2e-2
 
 
-def test_conv_group2():
+@pytest.mark.parametrize("C,O", [(32, 64), (96, 256)])
+def test_conv_group2(C, O):
     torch.manual_seed(5)
-    N, H, W, C, O = 2, 13, 13, 32, 64
+    N, H, W = 2, 13, 13
     x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16).requires_grad_(True)
     ws = [(torch.randn(O // 2, 3, 3, C // 2, device=DEV) * 0.1).to(torch.bfloat16).requires_grad_(True) for _ in range(2)]
     bs = [torch.randn(O // 2, device=DEV).requires_grad_(True) for _ in range(2)]

@@ -45,7 +45,13 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
                long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
                cudaStream_t st);
 
+void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, cudaStream_t st);
+void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
+                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st);
+
 // ---- nn_kernels.cu
+void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cudaStream_t st);
 void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
 void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
 void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st);

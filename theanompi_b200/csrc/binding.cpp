@@ -17,6 +17,7 @@ typedef uintptr_t ptr_t;
 
 static inline void* P(ptr_t p) { return reinterpret_cast<void*>(p); }
 static inline cudaStream_t S(ptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline cudaStream_t S_(ptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 static GroupTable make_table(const std::vector<float>& lr_mult, const std::vector<float>& wd, const std::vector<int>& exch) {
   GroupTable t;
@@ -51,6 +52,16 @@ PYBIND11_MODULE(_tmpi_native, m) {
     gemm_bf16(P(A), P(B), P(C), (const float*)P(bias), M, N, K, lda, ldb, ldc, a_mn, b_mn, out_bf16, bias_mode, relu, alpha, bn_hint,
               splitk, S(st));
   });
+
+  m.def("conv_fprop", [](ptr_t x, ptr_t w, ptr_t y, ptr_t bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo,
+                         int S, int Pd, int O, long long ldc, int relu, int out_bf16, ptr_t st) {
+    conv_fprop_bf16(P(x), P(w), P(y), (const float*)P(bias), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldc, relu, out_bf16, S_(st));
+  });
+  m.def("conv_wgrad", [](ptr_t dy, ptr_t x, ptr_t dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int S,
+                         int Pd, int O, long long ldy, ptr_t st) {
+    conv_wgrad_bf16(P(dy), P(x), P(dw), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldy, S_(st));
+  });
+  m.def("conv_weight_flip", [](ptr_t w, ptr_t wt, int O, int KH, int KW, int Cg, ptr_t st) { conv_weight_flip(P(w), P(wt), O, KH, KW, Cg, S_(st)); });
 
   // ---------------------------------------------------------------- layer kernels
   m.def("lrn_fwd", [](ptr_t x, ptr_t y, long long rows, int C, int n, float k, float alpha, float beta, ptr_t st) {

@@ -28,7 +28,8 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int NUM_EPI_WARPS = 8;
 
 template <int BN> struct Cfg {
   // persistent kernel, one CTA per SM: operand ring + a dedicated epilogue staging tile + 2 TMEM accumulators
@@ -55,6 +56,12 @@ struct Params {
   int relu;
   int kb_per_split;     // k-blocks per split-K slice
   int mt, nt, splits;   // tile grid (the kernel is persistent: tiles are walked round-robin by the CTAs)
+  int num_kb;           // total k-blocks (GEMM: ceil(K/64); conv: taps*chunks or pixel blocks)
+  // implicit-GEMM convolution (operands gathered by TMA im2col loads, no col matrix in memory):
+  //   conv_mode 1  fprop / dgrad : A = activation im2col tile [128 pixels x 64 ch] per (tap, chunk); B = weights [O][tap][C] 3-D tiled
+  //   conv_mode 2  wgrad         : A = dy (MN-major tiled);  B = activation im2col boxes [64 pixels x 64 ch]; n-tiles = (tap, channel chunk)
+  int conv_mode;
+  int cHo, cWo, cS, cP, cKH, cKW, cCg, c_chunks;
   int atomic_out;       // 1 = fp32 atomicAdd (split-K)
 };
 
@@ -96,6 +103,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// im2col-mode TMA on an NHWC tensor (dims C,W,H,N): coordinates are the input position of the window's top-left corner
+// (w = q*stride - pad, h = p*stride - pad) of the FIRST pixel of the tile; the filter tap goes in the 16-bit offsets.
+// The unit then walks pixelsPerColumn output positions (W, then H, then N) and zero-fills padding / out-of-range pixels.
+// (Semantics established with csrc/probe_im2col.cu on a B200.)
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                int off_w, int off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)off_w), "h"((uint16_t)off_h) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -165,7 +187,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb_total = (p.K + BK - 1) / BK;
+  const int num_kb_total = p.num_kb;
   const int tiles_mn = p.mt * p.nt;
   const int total_tiles = tiles_mn * p.splits;
 
@@ -173,7 +195,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 4); }
+    for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -191,24 +213,60 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int split = tile / tiles_mn, rem = tile % tiles_mn;
         const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
         const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+        // conv fprop/dgrad: decode the tile's first output pixel once
+        int img0 = 0, bw0 = 0, bh0 = 0;
+        if (p.conv_mode == 1) {
+          const int hw = p.cHo * p.cWo;
+          img0 = m0 / hw; const int r_ = m0 - img0 * hw; const int p0 = r_ / p.cWo, q0 = r_ - p0 * p.cWo;
+          bw0 = q0 * p.cS - p.cP; bh0 = p0 * p.cS - p.cP;
+        }
+        int w_tap = 0, w_c0 = 0;
+        if (p.conv_mode == 2) {                       // n-tile = (tap, channel chunk)
+          const int nblk = rem / p.mt;
+          w_tap = nblk / p.c_chunks; w_c0 = (nblk - w_tap * p.c_chunks) * BN;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
-          } else {
+          if (p.conv_mode == 1) {
+            const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
+            const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            tma_load_im2col(sa, &tmap_a, full_bar(stage), cc * BK, bw0, bh0, img0, s_, r_);      // [128 pixels x 64 ch]
+            tma_load_3d(sb, &tmap_b, full_bar(stage), cc * BK, tap, n0);                          // [BN out-ch x 64 ch]
+          } else if (p.conv_mode == 2) {
+            const int hw = p.cHo * p.cWo;
+            const int pix = kb * BK;
+            const int img = pix / hw; const int r2 = pix - img * hw; const int pp = r2 / p.cWo, qq = r2 - pp * p.cWo;
+            const int r_ = w_tap / p.cKW, s_ = w_tap - r_ * p.cKW;
+            int nbox = 0;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
-              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
-          }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
-          } else {
+            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) if (w_c0 + 64 * j < p.cCg) ++nbox;
+            mbar_expect_tx(full_bar(stage), C::A_BYTES + nbox * (BK * 128));
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)                                        // dy, MN-major: box {64 m, 64 pixels}
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, pix);
 #pragma unroll
             for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+              if (w_c0 + 64 * j < p.cCg)                                              // [64 pixels x 64 ch] at this tap
+                tma_load_im2col(sb + j * (BK * 128), &tmap_b, full_bar(stage), w_c0 + 64 * j, qq * p.cS - p.cP, pp * p.cS - p.cP, img, s_, r_);
+          } else {
+            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
+                tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
+            }
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
+                tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+            }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -256,7 +314,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     __syncwarp();
   } else {
     // ===================== epilogue: TMEM → registers → smem staging → global =====================
-    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    // 8 warps: warp w reads TMEM lane quarter q = w % 4 (hardware rule) and the column half (w - 2) / 4 of the tile.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int COLS_PER_WARP = (BN >= 64) ? BN / 2 : BN;          // BN = 32: only the first four warps carry data
+    const bool active = (BN >= 64) || half == 0;
+    const int col0 = (BN >= 64) ? half * COLS_PER_WARP : 0;
     const int row = 32 * q + lane;                 // row inside the tile
     const int esz = p.out_bf16 ? 2 : 4;
     const uint32_t pitch = (uint32_t)(BN * esz + 16);
@@ -264,43 +327,57 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int rem = tile % tiles_mn;
-      const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
+      const int m0 = (rem % p.mt) * BM;
+      int n0 = (rem / p.mt) * BN, n_end = p.N;
+      if (p.conv_mode == 2) {                        // wgrad: columns of this tile belong to ONE filter tap
+        const int nblk = rem / p.mt;
+        const int tap = nblk / p.c_chunks, c0 = (nblk - tap * p.c_chunks) * BN;
+        n0 = tap * p.cCg + c0;
+        n_end = tap * p.cCg + min(p.cCg, c0 + BN);
+      }
       const int acc = t & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
       mbar_wait(tmem_full_bar(acc), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if (!active) {                               // nothing to read: just hand the accumulator back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        continue;
+      }
       const int m = m0 + row;
       const bool m_ok = m < p.M;
       float bias_m = 0.f;
       if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
-      // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores.
-      const bool staged = !p.atomic_out && (n0 + BN <= p.N) && (((long long)p.ldc * esz) % 16 == 0) &&
+      // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores
+      // (plain stores, or vector reductions red.global.add.v4.f32 for split-K).
+      const bool staged = (n0 + BN <= n_end) && (((long long)p.ldc * esz) % 16 == 0) &&
                           ((reinterpret_cast<uintptr_t>(p.C) + (long long)n0 * esz) % 16 == 0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         uint32_t r[32];
+        const int cc = col0 + 32 * c;                // column offset inside the tile
         __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(32 * c), r);
+        tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, r);
         tmem_ld_wait();
-        if (c == BN / 32 - 1) {
+        if (c == COLS_PER_WARP / 32 - 1) {
           // all of this warp's TMEM reads for the tile are done → hand the accumulator back to the MMA thread
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
-        const int nb = n0 + 32 * c;
-        if (!staged && (!m_ok || nb >= p.N)) continue;
+        const int nb = n0 + cc;
+        if (!staged && (!m_ok || nb >= n_end)) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(r[j]) * p.alpha;
-          if (p.bias_mode == 1) { x += (nb + j < p.N) ? __ldg(p.bias + nb + j) : 0.f; }
+          if (p.bias_mode == 1) { x += (nb + j < n_end) ? __ldg(p.bias + nb + j) : 0.f; }
           else if (p.bias_mode == 2) { x += bias_m; }
           if (p.relu) x = fmaxf(x, 0.f);
           v[j] = x;
         }
         if (staged) {
-          uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)(32 * c) * esz;
+          uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)cc * esz;
           if (p.out_bf16) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
@@ -310,11 +387,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           continue;
         }
-        const bool full = (nb + 32 <= p.N);
+        const bool full = (nb + 32 <= n_end);
         if (p.atomic_out) {
           float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (full || nb + j < p.N) atomicAdd(dst + j, v[j]);
+          for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
         } else if (p.out_bf16) {
           __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
           if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -322,7 +399,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = f_to_bf16(v[j]);
+            for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = f_to_bf16(v[j]);
           }
         } else {
           float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
@@ -331,25 +408,31 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < p.N) dst[j] = v[j];
+            for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = v[j];
           }
         }
       }
       if (staged) {
-        // each warp re-reads only the 32 rows it staged itself → a warp-level sync is enough
+        // each warp re-reads only the (32 rows x its column half) it staged itself → a warp-level sync is enough
         __syncwarp();
-        const int vec_per_row = (BN * esz) / 16;                 // 16-byte vectors per tile row (<= 32)
+        const int vec_per_row = (COLS_PER_WARP * esz) / 16;      // 16-byte vectors per row of this warp's region (<= 32)
         const int rows_per_it = 32 / vec_per_row;
-        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)n0 * esz;
+        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)(n0 + col0) * esz;
         const int lr = lane / vec_per_row, lv = lane % vec_per_row;
         for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
           const int rr = 32 * q + r0 + lr;
           if (m0 + rr < p.M) {
-            const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + (size_t)rr * pitch + (size_t)lv * 16);
-            *reinterpret_cast<uint4*>(gbase + (long long)(m0 + rr) * p.ldc * esz + (long long)lv * 16) = val;
+            const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + (size_t)rr * pitch + (size_t)col0 * esz + (size_t)lv * 16);
+            uint8_t* gp = gbase + (long long)(m0 + rr) * p.ldc * esz + (long long)lv * 16;
+            if (p.atomic_out) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(val.x)),
+                           "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
+            } else {
+              *reinterpret_cast<uint4*>(gp) = val;
+            }
           }
         }
-        __syncwarp();                                            // staging rows are free for the next tile
+        __syncwarp();                                            // staging region is free for the next tile
       }
     }
   }
@@ -430,16 +513,22 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   if (M <= 0 || N <= 0 || K <= 0) return;
   const int sms = sm_count();
   const int mt = (M + BM - 1) / BM;
+  const bool can_split = (!out_bf16) && bias_mode == 0 && !relu;
   int BN = bn_hint;
   if (BN == 0) {
     BN = 128;
-    if (mt * ((N + 127) / 128) < sms && N >= 64) BN = 64;
-    if (BN == 64 && mt * ((N + 63) / 64) < sms && !b_mn && N >= 32) BN = 32;
+    // Narrow tiles only buy parallelism when split-K cannot (fused bias/ReLU or bf16 output): with split-K available the
+    // wide tile is always better — every extra n-tile re-reads the whole A operand through L2.
+    if (!(can_split && splitk != 1)) {
+      if (mt * ((N + 127) / 128) < sms && N >= 64) BN = 64;
+      if (BN == 64 && mt * ((N + 63) / 64) < sms && !b_mn && N >= 32) BN = 32;
+    } else if (N <= 64) {
+      BN = 64;
+    }
   }
   if (b_mn && BN < 64) BN = 64;
   const int nt = (N + BN - 1) / BN;
   const int num_kb = (K + BK - 1) / BK;
-  const bool can_split = (!out_bf16) && bias_mode == 0 && !relu;
   int splits = 1;
   if (splitk > 1 && can_split) splits = splitk;
   else if (splitk == 0 && can_split && mt * nt < sms && num_kb >= 8) {
@@ -453,7 +542,8 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   Params p;
   p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
-  p.mt = mt; p.nt = nt; p.splits = splits;
+  p.mt = mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
+  p.cHo = p.cWo = p.cS = p.cP = p.cKH = p.cKW = p.cCg = p.c_chunks = 0;
   if (splits > 1) {
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
     check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");
@@ -465,6 +555,127 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   if (BN == 128) launch<128>(ta, tb, p, splits, st);
   else if (BN == 64) launch<64>(ta, tb, p, splits, st);
   else launch<32>(ta, tb, p, splits, st);
+}
+
+// ------------------------------------------------------------------ implicit-GEMM convolution (TMA im2col)
+namespace gemm {
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const int*,
+                                     const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeIm2col get_encode_im2col() {
+  static PFN_encodeIm2col fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeIm2col)f;
+    (void)cudaGetLastError();
+  });
+  if (!fn) throw std::runtime_error("tmpi_native: cuTensorMapEncodeIm2col unavailable");
+  return fn;
+}
+
+// NHWC activation (channel slice [c_off, c_off+Cg) of a tensor with Ctot channels) as an im2col tensor map:
+// box = pixels x 64 channels, 128 B swizzle, zero fill for padding / out-of-range pixels / channels >= Cg.
+static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int S, int P, int pixels) {
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x) + c_off;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (Ctot % 8) != 0) throw std::runtime_error("tmpi_native: im2col operand must be 16B aligned");
+  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{base, N, H, W, Ctot, Cg, KH, KW, S, P, pixels};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)Cg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Ctot * 2, (cuuint64_t)W * Ctot * 2, (cuuint64_t)H * W * Ctot * 2};
+  int lower[2] = {-P, -P};
+  int upper[2] = {P - (KW - 1), P - (KH - 1)};
+  cuuint32_t estr[4] = {1u, (cuuint32_t)S, (cuuint32_t)S, 1u};
+  CUresult r = get_encode_im2col()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, lower, upper,
+                                   64u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeIm2col failed, code " + std::to_string((int)r));
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+
+// weights [O][KH*KW][Cg] (bf16, contiguous) as a 3-D tiled map, box {64 ch, 1 tap, box_o out-channels}
+static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o) {
+  if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (Cg % 8) != 0) throw std::runtime_error("tmpi_native: conv weights must be 16B aligned, C % 8 == 0");
+  using Key = std::tuple<const void*, int, int, int, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key{w, O, taps, Cg, box_o};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  CUtensorMap m;
+  cuuint64_t dims[3] = {(cuuint64_t)Cg, (cuuint64_t)taps, (cuuint64_t)O};
+  cuuint64_t strides[2] = {(cuuint64_t)Cg * 2, (cuuint64_t)taps * Cg * 2};
+  cuuint32_t box[3] = {64u, 1u, (cuuint32_t)box_o};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled(3D weights) failed, code " + std::to_string((int)r));
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  return m;
+}
+}  // namespace gemm
+
+// y[N*Ho*Wo, O] (ld = ldc, bf16) = relu(conv(x[.., c_off:c_off+Cg], w[O][KH][KW][Cg]) + bias)   — no col matrix in memory
+void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, cudaStream_t st) {
+  using namespace gemm;
+  const long long M = (long long)N * Ho * Wo;
+  if (M <= 0 || O <= 0) return;
+  if (M >= (1LL << 31)) throw std::runtime_error("conv_fprop: too many output pixels");
+  const int BN = O > 64 ? 128 : 64;
+  Params p;
+  p.C = y; p.bias = bias; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = 0;
+  p.out_bf16 = out_bf16; p.bias_mode = bias ? 1 : 0; p.relu = relu; p.atomic_out = 0;
+  p.mt = (int)((M + BM - 1) / BM); p.nt = (O + BN - 1) / BN; p.splits = 1;
+  p.conv_mode = 1; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BK - 1) / BK;
+  p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
+  CUtensorMap ta = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BM);
+  CUtensorMap tb = make_weight_map(w, O, KH * KW, Cg, BN);
+  if (BN == 128) launch<128>(ta, tb, p, 1, st); else launch<64>(ta, tb, p, 1, st);
+}
+
+// dw[O][KH*KW][Cg] (fp32, contiguous) = sum over pixels dy[pix, o] * im2col(x)[pix, (tap, c)]   (dy: [M, O] bf16, row pitch ldy)
+void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
+                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+  using namespace gemm;
+  const long long M = (long long)N * Ho * Wo;
+  if (M <= 0 || O <= 0) return;
+  if (M >= (1LL << 31)) throw std::runtime_error("conv_wgrad: too many output pixels");
+  const int sms = sm_count();
+  const int BN = Cg > 64 ? 128 : 64;
+  Params p;
+  p.C = dw; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
+  p.out_bf16 = 0; p.bias_mode = 0; p.relu = 0;
+  p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BN - 1) / BN;
+  p.mt = (O + BM - 1) / BM; p.nt = KH * KW * p.c_chunks;
+  p.num_kb = (int)((M + BK - 1) / BK);
+  int splits = 1;
+  const int tiles = p.mt * p.nt;
+  if (tiles < sms && p.num_kb >= 8) {
+    splits = (sms + tiles - 1) / tiles;
+    if (splits > p.num_kb / 4) splits = p.num_kb / 4;
+    if (splits < 1) splits = 1;
+  }
+  p.kb_per_split = (p.num_kb + splits - 1) / splits;
+  splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
+  p.splits = splits; p.atomic_out = splits > 1;
+  if (splits > 1) check_cuda(cudaMemsetAsync(dw, 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
+  CUtensorMap ta = make_tmap(dy, (uint64_t)O, (uint64_t)M, (uint64_t)ldy * 2, 64u);
+  CUtensorMap tb = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BK);
+  if (BN == 128) launch<128>(ta, tb, p, splits, st); else launch<64>(ta, tb, p, splits, st);
 }
 
 }  // namespace tmpi

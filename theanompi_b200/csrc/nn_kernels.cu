@@ -6,6 +6,7 @@
 // Softmax :937-997, Crop/Subtract :223-347) and data/utils.py:42-129 (crop_and_mirror).
 #include "common.cuh"
 #include "api.h"
+#include <algorithm>
 
 namespace tmpi {
 
@@ -126,10 +127,10 @@ struct PoolGeom { int N, H, W, C, Ho, Wo, k, s, p; };
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ arg, PoolGeom g) {
   const int nvec = g.C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)g.N * g.Ho * g.Wo * nvec;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;             // host guarantees total < 2^32
+  const unsigned total = (unsigned)g.N * g.Ho * g.Wo * nvec;
   if (idx >= total) return;
-  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int cv = (int)(idx % (unsigned)nvec); unsigned t = idx / (unsigned)nvec;
   const int wo = (int)(t % g.Wo); t /= g.Wo;
   const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
   float best[8]; int bi[8];
@@ -158,10 +159,10 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
                                    __nv_bfloat16* __restrict__ dx, PoolGeom g) {
   const int nvec = g.C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)g.N * g.H * g.W * nvec;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;             // host guarantees total < 2^32
+  const unsigned total = (unsigned)g.N * g.H * g.W * nvec;
   if (idx >= total) return;
-  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int cv = (int)(idx % (unsigned)nvec); unsigned t = idx / (unsigned)nvec;
   const int w = (int)(t % g.W); t /= g.W;
   const int h = (int)(t % g.H); const int n = (int)(t / g.H);
   float acc[8];
@@ -201,10 +202,10 @@ __device__ __forceinline__ int avg_count(const PoolGeom& g, int ho, int wo) {
 
 __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, PoolGeom g) {
   const int nvec = g.C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)g.N * g.Ho * g.Wo * nvec;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;             // host guarantees total < 2^32
+  const unsigned total = (unsigned)g.N * g.Ho * g.Wo * nvec;
   if (idx >= total) return;
-  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int cv = (int)(idx % (unsigned)nvec); unsigned t = idx / (unsigned)nvec;
   const int wo = (int)(t % g.Wo); t /= g.Wo;
   const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
   float acc[8];
@@ -230,10 +231,10 @@ __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 
 __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, PoolGeom g) {
   const int nvec = g.C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)g.N * g.H * g.W * nvec;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;             // host guarantees total < 2^32
+  const unsigned total = (unsigned)g.N * g.H * g.W * nvec;
   if (idx >= total) return;
-  const int cv = (int)(idx % nvec); long long t = idx / nvec;
+  const int cv = (int)(idx % (unsigned)nvec); unsigned t = idx / (unsigned)nvec;
   const int w = (int)(t % g.W); t /= g.W;
   const int h = (int)(t % g.H); const int n = (int)(t / g.H);
   float acc[8];
@@ -261,6 +262,7 @@ void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int
   if (C % 8) throw std::runtime_error("pool: C must be a multiple of 8");
   PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
   long long total = (long long)N * Ho * Wo * (C / 8);
+  if ((long long)N * H * W * (C / 8) >= (1LL << 32)) throw std::runtime_error("pool: tensor too large for 32-bit indexing");
   if (is_max) maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)arg, g);
   else avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
   count_launch(); TMPI_CHECK_LAUNCH("pool_fwd"); ::tmpi::check_capture(st, "pool_fwd");
@@ -662,6 +664,23 @@ void transpose_bf16(const void* src, void* dst, int R, int C, cudaStream_t st) {
   dim3 grid((C + 31) / 32, (R + 31) / 32), block(32, 8);
   transpose_bf16_kernel<<<grid, block, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, R, C);
   count_launch(); TMPI_CHECK_LAUNCH("transpose_bf16"); ::tmpi::check_capture(st, "transpose_bf16");
+}
+
+// dgrad of a stride-1 convolution is a forward convolution of dy with the spatially flipped, channel-transposed filter:
+// wt[c][KH-1-r][KW-1-s][o] = w[o][r][s][c]     (tiny: runs once per layer per step)
+__global__ void conv_weight_flip_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wt, int O, int KH, int KW, int Cg) {
+  const int total = O * KH * KW * Cg;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o = i % O; int t = i / O;                      // iterate over the OUTPUT layout [c][r'][s'][o] (coalesced writes)
+    const int s2 = t % KW; t /= KW;
+    const int r2 = t % KH; const int c = t / KH;
+    wt[i] = w[(((long long)o * KH + (KH - 1 - r2)) * KW + (KW - 1 - s2)) * Cg + c];
+  }
+}
+void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cudaStream_t st) {
+  const int total = O * KH * KW * Cg;
+  conv_weight_flip_kernel<<<std::min(grid_for(total, 256), sm_count() * 8), 256, 0, st>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)wt, O, KH, KW, Cg);
+  count_launch(); TMPI_CHECK_LAUNCH("conv_weight_flip"); ::tmpi::check_capture(st, "conv_weight_flip");
 }
 
 // ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32

@@ -14,6 +14,8 @@ Everything raises if the extension is missing — there is no eager fallback on 
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import native
@@ -176,11 +178,28 @@ def _w2d(w, K, Kp):
     return wp
 
 
+CONV_MODE = os.environ.get("TMPI_CONV", "implicit")      # implicit: TMA-im2col implicit GEMM; explicit: im2col matrix + GEMM
+
+
+def _implicit_ok(x, w, c_off, Cg, Ot, o_off):
+    """TMA im2col needs 16-byte aligned channel slices; C = 3 (first layer) stays on the explicit path."""
+    Ct = x.shape[3]
+    return (CONV_MODE == "implicit" and Cg % 8 == 0 and c_off % 8 == 0 and Ct % 8 == 0 and Ot % 8 == 0 and o_off % 8 == 0
+            and w.shape[0] % 8 == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0)
+
+
 def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
     N, H, W, Ct = x.shape
     Og, KH, KW, _ = w.shape
     Ho, Wo = y.shape[1], y.shape[2]
     Ot = y.shape[3]
+    wb = _bf(w)
+    if _implicit_ok(x, wb, c_off, Cg, Ot, o_off):
+        # implicit GEMM: the activation tile is gathered by TMA im2col loads inside the kernel — no col matrix
+        yp = y.data_ptr() + o_off * 2
+        L().conv_fprop(x.data_ptr(), wb.data_ptr(), yp, _p(b), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
+                       Og, Ot, int(bool(relu)), 1, _st(x))
+        return None
     col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
     w2 = _w2d(w, K, Kp)
     M = N * Ho * Wo
@@ -224,6 +243,25 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
     dyv = dy.view(M, Ot)[:, o_off:o_off + Og]
     yv = y.view(M, Ot)[:, o_off:o_off + Og]
     dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
+    wb = _bf(w)
+    if col is None and _implicit_ok(x, wb, c_off, Cg, Ot, o_off):
+        # ---- implicit GEMM backward: wgrad gathers im2col(x) by TMA; dgrad (stride 1) is a forward conv of dy with the
+        # flipped / transposed filter, written straight into dx's channel slice.
+        dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
+        L().conv_wgrad(dym.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
+                       Og, Og, _st(x))
+        if need_dx:
+            if s == 1:
+                wt = torch.empty((Cg, KH, KW, Og), dtype=BF16, device=dev)
+                L().conv_weight_flip(wb.data_ptr(), wt.data_ptr(), Og, KH, KW, int(Cg), _st(x))
+                L().conv_fprop(dym.data_ptr(), wt.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, Og, 0, Og, KH, KW, H, W, 1,
+                               KH - 1 - int(p), int(Cg), Ct, 0, 1, _st(x))
+            else:
+                colK = KH * KW * Cg
+                Kp = (colK + 7) // 8 * 8
+                dcol = gemm(dym, _w2d(w, colK, Kp), M, Kp, Og, b_mn=True, lda=Og, ldb=Kp)
+                L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+        return dw, db
     col, Kp, K = col if col is not None else _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)   # forward's matrix is reused
     dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
     # wgrad: dW[Og, K] = dymᵀ[Og, M] · col[M, K]   (both operands MN-major, split-K over M)

@@ -51,6 +51,8 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
                      int Wo, int S, int P, int O, long long ldy, cudaStream_t st);
 
 // ---- nn_kernels.cu
+void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st);
+void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, cudaStream_t st);
 void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cudaStream_t st);
 void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
 void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);

@@ -61,6 +61,10 @@ PYBIND11_MODULE(_tmpi_native, m) {
                          int Pd, int O, long long ldy, ptr_t st) {
     conv_wgrad_bf16(P(dy), P(x), P(dw), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldy, S_(st));
   });
+  m.def("space_to_depth", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, ptr_t st) {
+    space_to_depth(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, S_(st)); });
+  m.def("s2d_filter", [](ptr_t src, ptr_t dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, ptr_t st) {
+    s2d_filter(P(src), P(dst), O, KH, KW, C, S, KHs, KWs, Cp, dir, S_(st)); });
   m.def("conv_weight_flip", [](ptr_t w, ptr_t wt, int O, int KH, int KW, int Cg, ptr_t st) { conv_weight_flip(P(w), P(wt), O, KH, KW, Cg, S_(st)); });
 
   // ---------------------------------------------------------------- layer kernels

@@ -220,11 +220,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           img0 = m0 / hw; const int r_ = m0 - img0 * hw; const int p0 = r_ / p.cWo, q0 = r_ - p0 * p.cWo;
           bw0 = q0 * p.cS - p.cP; bh0 = p0 * p.cS - p.cP;
         }
-        int w_tap = 0, w_c0 = 0;
-        if (p.conv_mode == 2) {                       // n-tile = (tap, channel chunk)
-          const int nblk = rem / p.mt;
-          w_tap = nblk / p.c_chunks; w_c0 = (nblk - w_tap * p.c_chunks) * BN;
-        }
+        int w_box0 = 0;
+        if (p.conv_mode == 2) w_box0 = (rem / p.mt) * (BN >= 64 ? BN / 64 : 1);    // n-tile = BN/64 consecutive (tap, 64-channel) boxes
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
@@ -239,18 +236,23 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const int hw = p.cHo * p.cWo;
             const int pix = kb * BK;
             const int img = pix / hw; const int r2 = pix - img * hw; const int pp = r2 / p.cWo, qq = r2 - pp * p.cWo;
-            const int r_ = w_tap / p.cKW, s_ = w_tap - r_ * p.cKW;
+            const int total_boxes = p.cKH * p.cKW * p.c_chunks;
             int nbox = 0;
 #pragma unroll
-            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) if (w_c0 + 64 * j < p.cCg) ++nbox;
+            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) if (w_box0 + j < total_boxes) ++nbox;
             mbar_expect_tx(full_bar(stage), C::A_BYTES + nbox * (BK * 128));
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)                                        // dy, MN-major: box {64 m, 64 pixels}
               tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, pix);
 #pragma unroll
-            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-              if (w_c0 + 64 * j < p.cCg)                                              // [64 pixels x 64 ch] at this tap
-                tma_load_im2col(sb + j * (BK * 128), &tmap_b, full_bar(stage), w_c0 + 64 * j, qq * p.cS - p.cP, pp * p.cS - p.cP, img, s_, r_);
+            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) {
+              const int box = w_box0 + j;
+              if (box < total_boxes) {                                                // [64 pixels x 64 ch] of one filter tap
+                const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
+                const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
+                tma_load_im2col(sb + j * (BK * 128), &tmap_b, full_bar(stage), c64 * 64, qq * p.cS - p.cP, pp * p.cS - p.cP, img, s_, r_);
+              }
+            }
           } else {
             mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
             if (!p.a_mn) {
@@ -328,12 +330,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int rem = tile % tiles_mn;
       const int m0 = (rem % p.mt) * BM;
-      int n0 = (rem / p.mt) * BN, n_end = p.N;
-      if (p.conv_mode == 2) {                        // wgrad: columns of this tile belong to ONE filter tap
-        const int nblk = rem / p.mt;
-        const int tap = nblk / p.c_chunks, c0 = (nblk - tap * p.c_chunks) * BN;
-        n0 = tap * p.cCg + c0;
-        n_end = tap * p.cCg + min(p.cCg, c0 + BN);
+      int n0 = (rem / p.mt) * BN, n_end = p.N;       // global column of tile column cc is n0 + cc
+      if (p.conv_mode == 2) {
+        // wgrad: every 64-column box of the tile is one (filter tap, 64-channel chunk); this warp's columns [col0, col0+64)
+        // are exactly one box, which lands at column tap*Cg + c64*64 of dW.
+        const int box = (rem / p.mt) * (BN >= 64 ? BN / 64 : 1) + col0 / 64;
+        if (box < p.cKH * p.cKW * p.c_chunks) {
+          const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
+          n0 = tap * p.cCg + c64 * 64 - col0;
+          n_end = tap * p.cCg + min(p.cCg, c64 * 64 + 64);
+        } else {
+          n0 = 0; n_end = 0;
+        }
       }
       const int acc = t & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
@@ -350,8 +358,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
       // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores
       // (plain stores, or vector reductions red.global.add.v4.f32 for split-K).
-      const bool staged = (n0 + BN <= n_end) && (((long long)p.ldc * esz) % 16 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(p.C) + (long long)n0 * esz) % 16 == 0);
+      const bool staged = (n0 + col0 + COLS_PER_WARP <= n_end) && (((long long)p.ldc * esz) % 16 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.C) + (long long)(n0 + col0) * esz) % 16 == 0);
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         uint32_t r[32];
@@ -655,12 +663,12 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
   if (M <= 0 || O <= 0) return;
   if (M >= (1LL << 31)) throw std::runtime_error("conv_wgrad: too many output pixels");
   const int sms = sm_count();
-  const int BN = Cg > 64 ? 128 : 64;
+  const int BN = 128;                                  // two (tap, 64-channel) boxes per n-tile: halves the re-reads of dy
   Params p;
   p.C = dw; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
   p.out_bf16 = 0; p.bias_mode = 0; p.relu = 0;
-  p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BN - 1) / BN;
-  p.mt = (O + BM - 1) / BM; p.nt = KH * KW * p.c_chunks;
+  p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + 63) / 64;
+  p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / 64 - 1) / (BN / 64);
   p.num_kb = (int)((M + BK - 1) / BK);
   int splits = 1;
   const int tiles = p.mt * p.nt;

@@ -683,6 +683,71 @@ void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cu
   count_launch(); TMPI_CHECK_LAUNCH("conv_weight_flip"); ::tmpi::check_capture(st, "conv_weight_flip");
 }
 
+// ============================================================================ space-to-depth for strided few-channel convs
+// A KHxKW / stride-S convolution on C (< 8) channels is the ceil(KH/S) x ceil(KW/S) / stride-1 convolution of the
+// space-to-depth image x'[n, i, j, (dy*S+dx)*C + c] = x[n, S*i+dy, S*j+dx, c] with the re-indexed (zero padded) filter.
+// That turns AlexNet's conv1 (11x11/4 on RGB, which TMA cannot gather: 6-byte pixels) into a 3x3 conv on 48 channels
+// that runs on the implicit-GEMM tcgen05 path.
+__global__ void space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int S,
+                                      int Hs, int Ws, int Cp) {
+  const long long total = (long long)N * Hs * Ws * S;                 // one thread per (output pixel, dy): S*C contiguous inputs
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int dy = (int)(idx % S); long long t = idx / S;
+    const int j = (int)(t % Ws); t /= Ws;
+    const int i = (int)(t % Hs); const int n = (int)(t / Hs);
+    const int h = i * S + dy;
+    __nv_bfloat16* dst = y + (((long long)n * Hs + i) * Ws + j) * Cp + dy * S * C;
+    const __nv_bfloat16* src = x + (((long long)n * H + h) * W + (long long)j * S) * C;
+    for (int e = 0; e < S * C; ++e) {
+      const int w = j * S + e / C;
+      dst[e] = (h < H && w < W) ? src[e] : f_to_bf16(0.f);
+    }
+    if (dy == 0) for (int e = S * S * C; e < Cp; ++e) dst[e] = f_to_bf16(0.f);      // channel padding (Cp multiple of 8)
+  }
+}
+void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st) {
+  const long long total = (long long)N * Hs * Ws * S;
+  space_to_depth_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, S, Hs, Ws, Cp);
+  count_launch(); TMPI_CHECK_LAUNCH("space_to_depth"); ::tmpi::check_capture(st, "space_to_depth");
+}
+
+// w [O][KH][KW][C]  <->  ws [O][KHs][KWs][Cp]   with  ws[o, a, b, (dy*S+dx)*C + c] = w[o, S*a+dy, S*b+dx, c]  (0 outside the filter)
+// dir 0: pack bf16 filter (w -> ws);  dir 1: unpack fp32 gradient (gs -> g)
+__global__ void s2d_filter_kernel(const void* __restrict__ src, void* __restrict__ dst, int O, int KH, int KW, int C, int S, int KHs, int KWs,
+                                  int Cp, int dir) {
+  if (dir == 0) {
+    const int total = O * KHs * KWs * Cp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int cp = i % Cp; int t = i / Cp;
+      const int b = t % KWs; t /= KWs;
+      const int a = t % KHs; const int o = t / KHs;
+      __nv_bfloat16 v = f_to_bf16(0.f);
+      if (cp < S * S * C) {
+        const int c = cp % C, d = cp / C, dy = d / S, dx = d % S;
+        const int kh = a * S + dy, kw = b * S + dx;
+        if (kh < KH && kw < KW) v = reinterpret_cast<const __nv_bfloat16*>(src)[(((long long)o * KH + kh) * KW + kw) * C + c];
+      }
+      reinterpret_cast<__nv_bfloat16*>(dst)[i] = v;
+    }
+  } else {
+    const int total = O * KH * KW * C;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+      const int c = i % C; int t = i / C;
+      const int kw = t % KW; t /= KW;
+      const int kh = t % KH; const int o = t / KH;
+      const int a = kh / S, dy = kh % S, b = kw / S, dx = kw % S;
+      reinterpret_cast<float*>(dst)[i] =
+          reinterpret_cast<const float*>(src)[(((long long)o * KHs + a) * KWs + b) * Cp + (dy * S + dx) * C + c];
+    }
+  }
+}
+void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, cudaStream_t st) {
+  const int total = dir == 0 ? O * KHs * KWs * Cp : O * KH * KW * C;
+  s2d_filter_kernel<<<std::min(grid_for(total, 256), sm_count() * 8), 256, 0, st>>>(src, dst, O, KH, KW, C, S, KHs, KWs, Cp, dir);
+  count_launch(); TMPI_CHECK_LAUNCH("s2d_filter"); ::tmpi::check_capture(st, "s2d_filter");
+}
+
 // ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32
 template <typename Tin, typename Tout>
 __global__ void crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode, float scale,

@@ -208,11 +208,59 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
     return (col, Kp, K)
 
 
+def _s2d_geom(H, W, C, KH, KW, stride, pad):
+    """Geometry of the space-to-depth rewrite of a strided few-channel conv, or None when it does not apply."""
+    if not (CONV_MODE == "implicit" and C < 8 and stride > 1 and pad == 0):
+        return None
+    S = stride
+    Hs, Ws = -(-H // S), -(-W // S)
+    KHs, KWs = -(-KH // S), -(-KW // S)
+    Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
+    if Hs - KHs + 1 != Ho or Ws - KWs + 1 != Wo:
+        return None
+    Cp = (S * S * C + 7) // 8 * 8
+    return S, Hs, Ws, KHs, KWs, Cp, Ho, Wo
+
+
+def _conv_s2d_fwd(x, w, b, relu, g):
+    """First-layer conv (e.g. AlexNet 11x11/4 on RGB) as a stride-1 conv on the space-to-depth image (implicit GEMM)."""
+    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo = g
+    N, H, W, C = x.shape
+    O, KH, KW, _ = w.shape
+    dev = x.device
+    xs = torch.empty((N, Hs, Ws, Cp), dtype=BF16, device=dev)
+    L().space_to_depth(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
+    ws = torch.empty((O, KHs, KWs, Cp), dtype=BF16, device=dev)
+    L().s2d_filter(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 0, _st(x))
+    y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=dev)
+    L().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), _p(b), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O,
+                   int(bool(relu)), 1, _st(x))
+    return y, xs
+
+
+def _conv_s2d_bwd(xs, w, y, dy, relu, g, dw_out, db_out):
+    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo = g
+    O, KH, KW, C = w.shape
+    N = xs.shape[0]
+    M = N * Ho * Wo
+    dev = xs.device
+    dym, db = _mask_and_bias_grad(dy.view(M, O), y.view(M, O), relu, db_out.view(-1) if db_out is not None else None, M, O, O)
+    dws = torch.empty((O, KHs, KWs, Cp), dtype=torch.float32, device=dev)
+    L().conv_wgrad(dym.data_ptr(), xs.data_ptr(), dws.data_ptr(), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O, _st(xs))
+    dw = dw_out if dw_out is not None else torch.empty((O, KH, KW, C), dtype=torch.float32, device=dev)
+    L().s2d_filter(dws.data_ptr(), dw.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 1, _st(xs))
+    return dw, db
+
+
 def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True, return_cols=False):
     x = _bf(x).contiguous()
     N, H, W, C = x.shape
     O, KH, KW, Cg = w.shape
     assert Cg * groups == C
+    g = _s2d_geom(H, W, C, KH, KW, stride, pad) if (groups == 1 and O % 8 == 0) else None
+    if g is not None:
+        y, xs = _conv_s2d_fwd(x, w, b, relu, g)
+        return (y, [("s2d", xs, g)]) if return_cols else y
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
     y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=x.device)
     Og = O // groups
@@ -282,6 +330,11 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
     dy = _bf(dy).contiguous()
     N, H, W, C = x.shape
     O, KH, KW, Cg = w.shape
+    if cols and isinstance(cols[0], tuple) and len(cols[0]) == 3 and isinstance(cols[0][0], str) and cols[0][0] == "s2d":
+        if need_dx:
+            raise RuntimeError("space-to-depth conv path is for the first layer only (no input gradient)")
+        dw, db = _conv_s2d_bwd(cols[0][1], w, y, dy, relu, cols[0][2], dw_out, db_out)
+        return None, dw, db
     if (Cg % 8 or O % 8) and need_dx:
         raise RuntimeError("conv dgrad needs channel counts that are multiples of 8")
     dx = torch.empty_like(x) if need_dx else None

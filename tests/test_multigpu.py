@@ -26,3 +26,44 @@ def test_fused_kernels_two_ranks():
 def test_bench_two_ranks_fused_matches_loss_scale():
     r = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "4", "--warmup", "3", port=29612)
     assert r.returncode == 0 and '"n_gpus": 2' in r.stdout, r.stdout[-4000:]
+
+
+def _run_rule(rule_cls, devices, cfg=None, env=None, timeout=600):
+    import subprocess
+    rule = rule_cls()
+    rule.model_config = dict(batch_size=64, file_batch_size=64, n_epochs=1, learning_rate=0.001, max_batches=12, printFreq=4,
+                             data_kwargs=dict(n_synthetic=2048, synthetic=True))
+    rule.model_config.update(cfg or {})
+    rule.env.update(env or {})
+    rule.init(devices=devices, modelfile="theanompi_b200.models.cifar10", modelclass="Cifar10_model")
+    try:
+        return rule.proc.wait(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        rule.proc.kill()
+        raise
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("strategy", ["fused", "nccl32", "p2p32", "asa32", "copper", "nccl16"])
+def test_rule_bsp_gpu(tmp_path, monkeypatch, strategy):
+    import theanompi_b200 as tm
+    monkeypatch.chdir(tmp_path)
+    tm.BSP.sync_type, tm.BSP.exch_strategy = "cdd", strategy
+    assert _run_rule(tm.BSP, ["cuda0", "cuda1"]) == 0
+    tm.BSP.exch_strategy = "fused"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_rule_easgd_gpu(tmp_path, monkeypatch):
+    import theanompi_b200 as tm
+    monkeypatch.chdir(tmp_path)
+    n = min(3, torch.cuda.device_count())
+    assert _run_rule(tm.EASGD, ["cuda%d" % i for i in range(n)], env={"TMPI_EASGD_TAU": "4"}) == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_rule_gosgd_gpu(tmp_path, monkeypatch):
+    import theanompi_b200 as tm
+    monkeypatch.chdir(tmp_path)
+    n = min(4, torch.cuda.device_count())
+    assert _run_rule(tm.GOSGD, ["cuda%d" % i for i in range(n)], cfg=dict(gosgd_p=0.3)) == 0

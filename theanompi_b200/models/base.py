@@ -28,6 +28,7 @@ import torch
 
 from .. import ops
 from ..parallel.arena import FlatArena
+from ..utils import nvtx
 from ..utils.opt import FlatSGD, SharedScalar, pre_model_iter_fn
 from .layers2 import Crop, Dropout, count_params
 
@@ -318,11 +319,13 @@ class ModelBase(object):
         img, labels = self.data.train_img_shard, self.data.train_labels_shard
         if self.subb_t == 0:
             recorder.start()
-            self.last_one_t = self._load_file_batch("train", self.current_t, img, labels,
-                                                    self.data.n_batch_train)
+            with nvtx.range("load"):
+                self.last_one_t = self._load_file_batch("train", self.current_t, img, labels,
+                                                        self.data.n_batch_train)
             recorder.end("wait")
         recorder.start()
-        cost, error = self.train_iter_fn(self.subb_t)
+        with nvtx.range("train_iter_fn"):
+            cost, error = self.train_iter_fn(self.subb_t)
         recorder.train_error(count, cost, error)
         recorder.end("calc")
         if self.monitor_grad and self.verbose:

@@ -26,6 +26,7 @@ import torch
 import torch.distributed as dist
 
 from . import exchanger_strategy as ES
+from ..utils import nvtx
 
 FUSED = {"fused": ("auto", False), "fused16": ("auto", True), "oneshot": ("oneshot", False),
          "oneshot16": ("oneshot", True), "twoshot": ("twoshot", False), "twoshot16": ("twoshot", True),
@@ -186,7 +187,7 @@ class BSP_Exchanger(object):
         self.comm.Barrier()
         recorder.end("sync")
         recorder.start()
-        with torch.no_grad():
+        with torch.no_grad(), nvtx.range("exchange:" + self.exch_strategy):
             self.exch.exchange()
         if self.sync_type == "cdd":
             self.model.descent_vel()

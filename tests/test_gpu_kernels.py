@@ -140,6 +140,54 @@ def test_conv_group2(C, O):
     assert rel_err(torch.cat([b.grad for b in bs], 0), dbr) < 2e-2
 
 
+@pytest.mark.parametrize("groups,C,O,H,k,st,pd", [(1, 16, 64, 13, 3, 1, 1), (2, 32, 256, 15, 5, 1, 2), (1, 3, 96, 35, 11, 4, 0)])
+def test_conv_pool_fused_backward(groups, C, O, H, k, st, pd):
+    """conv(+ReLU)→max-pool block: the fused pool-scatter + ReLU-mask + bias-grad backward kernel vs the unfused
+    conv → pool2d composition and vs the fp32 reference."""
+    torch.manual_seed(11)
+    N = 2
+    pool = (3, 2, 0, "max")
+
+    def make():
+        torch.manual_seed(12)
+        x = torch.randn(N, H, H, C, device=DEV).to(torch.bfloat16).requires_grad_(C >= 8)
+        ws = [(torch.randn(O // groups, k, k, C // groups, device=DEV) * 0.1).to(torch.bfloat16).requires_grad_(True) for _ in range(groups)]
+        bs = [(torch.randn(O // groups, device=DEV) * 0.1).requires_grad_(True) for _ in range(groups)]
+        return x, ws, bs
+
+    def run(fused):
+        x, ws, bs = make()
+        pl = pool if fused else None
+        if groups == 1:
+            y = ops.conv2d_bias_act(x, ws[0], bs[0], st, pd, 1, True, pl)
+        else:
+            y = ops.conv2d_group2_bias_act(x, ws[0], bs[0], ws[1], bs[1], st, pd, True, pl)
+        if not fused:
+            y = ops.pool2d(y, *pool)
+        torch.manual_seed(13)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        return y, x.grad, torch.cat([w.grad for w in ws], 0), torch.cat([b.grad for b in bs], 0), dy
+
+    yf, dxf, dwf, dbf, dy = run(True)
+    yu, dxu, dwu, dbu, _ = run(False)
+    assert torch.equal(yf, yu)
+    assert rel_err(dwf, dwu) < 1e-3 and rel_err(dbf, dbu) < 1e-3
+    if dxf is not None:
+        assert rel_err(dxf, dxu) < 1e-3
+    # fp32 reference of the whole block
+    x, ws, bs = make()
+    xr = x.detach().float().requires_grad_(True)
+    wr = torch.cat([w.detach().float() for w in ws], 0).requires_grad_(True)
+    br = torch.cat([b.detach() for b in bs], 0).requires_grad_(True)
+    yr = ref.pool2d(ref.conv2d_bias_act(xr, wr, br, st, pd, groups, True), *pool)
+    yr.backward(dy.float())
+    assert rel_err(yf, yr) < 1e-2
+    assert rel_err(dwf, wr.grad) < 3e-2 and rel_err(dbf, br.grad) < 3e-2
+    if dxf is not None:
+        assert rel_err(dxf, xr.grad) < 3e-2
+
+
 @pytest.mark.parametrize("mode,k,s,p", [("max", 3, 2, 0), ("max", 2, 2, 0), ("max", 3, 1, 1), ("avg", 5, 3, 0), ("avg", 7, 1, 0)])
 def test_pool(mode, k, s, p):
     torch.manual_seed(6)

@@ -41,6 +41,7 @@ struct ReduceArgs {
 };
 
 // ---- gemm_tcgen05.cu
+void gemm_set_debug(int flags);   // bottleneck probe knobs of the tcgen05 GEMM (see Params::dbg)
 void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
                long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
                cudaStream_t st);
@@ -63,6 +64,8 @@ void dropout_bwd(const void* dy, const void* mask, void* dx, long long n, cudaSt
 void advance_step(void* step, cudaStream_t st);
 void softmax_xent(const void* logits, const void* labels, void* dlogits, void* rowstat, void* out3, int B, int C, float weight, cudaStream_t st);
 void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st);
+void maxpool_relu_bias_bwd(const void* dyp, const void* arg, const void* y, void* dym, void* db0, void* db1, int c_split, int N, int H,
+                           int W, int C, int Ho, int Wo, int k, int s, int p, cudaStream_t st);
 void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
             long long ldcol, cudaStream_t st);
 void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,

@@ -47,6 +47,7 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.attr("MAX_COMM_BLOCKS") = kMaxCommBlocks;
 
   // ---------------------------------------------------------------- GEMM
+  m.def("gemm_set_debug", &gemm_set_debug);
   m.def("gemm_bf16", [](ptr_t A, ptr_t B, ptr_t C, ptr_t bias, int M, int N, int K, long long lda, long long ldb, long long ldc,
                         int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk, ptr_t st) {
     gemm_bf16(P(A), P(B), P(C), (const float*)P(bias), M, N, K, lda, ldb, ldc, a_mn, b_mn, out_bf16, bias_mode, relu, alpha, bn_hint,
@@ -82,6 +83,9 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.def("advance_step", [](ptr_t step, ptr_t st) { advance_step(P(step), S(st)); });
   m.def("softmax_xent", [](ptr_t logits, ptr_t labels, ptr_t dlogits, ptr_t rowstat, ptr_t out3, int B, int C, float weight, ptr_t st) {
     softmax_xent(P(logits), P(labels), P(dlogits), P(rowstat), P(out3), B, C, weight, S(st)); });
+  m.def("maxpool_relu_bias_bwd", [](ptr_t dyp, ptr_t arg, ptr_t y, ptr_t dym, ptr_t db0, ptr_t db1, int c_split, int N, int H, int W, int C,
+                                    int Ho, int Wo, int k, int s, int p, ptr_t st) {
+    maxpool_relu_bias_bwd(P(dyp), P(arg), P(y), P(dym), P(db0), P(db1), c_split, N, H, W, C, Ho, Wo, k, s, p, S(st)); });
   m.def("relu_bias_bwd", [](ptr_t dy, ptr_t y, ptr_t dym, ptr_t db, long long R, int C, long long ld, int relu, ptr_t st) {
     relu_bias_bwd(P(dy), P(y), P(dym), P(db), R, C, ld, relu, S(st)); });
   m.def("im2col", [](ptr_t x, ptr_t col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,

@@ -63,6 +63,7 @@ struct Params {
   int conv_mode;
   int cHo, cWo, cS, cP, cKH, cKW, cCg, c_chunks;
   int atomic_out;       // 1 = fp32 atomicAdd (split-K)
+  int dbg;              // bottleneck probe (scripts/gemm_probe.py): 1 = skip A loads, 2 = skip B loads, 4 = skip the MMAs
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -209,6 +210,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const bool skip_a = (p.dbg & 1) != 0, skip_b = (p.dbg & 2) != 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int split = tile / tiles_mn, rem = tile % tiles_mn;
         const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
@@ -229,9 +231,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (p.conv_mode == 1) {
             const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
             const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
-            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-            tma_load_im2col(sa, &tmap_a, full_bar(stage), cc * BK, bw0, bh0, img0, s_, r_);      // [128 pixels x 64 ch]
-            tma_load_3d(sb, &tmap_b, full_bar(stage), cc * BK, tap, n0);                          // [BN out-ch x 64 ch]
+            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES));
+            if (!skip_a) tma_load_im2col(sa, &tmap_a, full_bar(stage), cc * BK, bw0, bh0, img0, s_, r_);      // [128 pixels x 64 ch]
+            if (!skip_b) tma_load_3d(sb, &tmap_b, full_bar(stage), cc * BK, tap, n0);                          // [BN out-ch x 64 ch]
           } else if (p.conv_mode == 2) {
             const int hw = p.cHo * p.cWo;
             const int pix = kb * BK;
@@ -240,29 +242,32 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             int nbox = 0;
 #pragma unroll
             for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) if (w_box0 + j < total_boxes) ++nbox;
-            mbar_expect_tx(full_bar(stage), C::A_BYTES + nbox * (BK * 128));
+            if (skip_b) nbox = 0;
+            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + nbox * (BK * 128));
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)                                        // dy, MN-major: box {64 m, 64 pixels}
-              tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, pix);
+              if (!skip_a) tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, pix);
 #pragma unroll
             for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) {
               const int box = w_box0 + j;
-              if (box < total_boxes) {                                                // [64 pixels x 64 ch] of one filter tap
+              if (box < total_boxes && !skip_b) {                                     // [64 pixels x 64 ch] of one filter tap
                 const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
                 const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
                 tma_load_im2col(sb + j * (BK * 128), &tmap_b, full_bar(stage), c64 * 64, qq * p.cS - p.cP, pp * p.cS - p.cP, img, s_, r_);
               }
             }
           } else {
-            mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-            if (!p.a_mn) {
+            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES));
+            if (skip_a) {
+            } else if (!p.a_mn) {
               tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
             } else {
 #pragma unroll
               for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
                 tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
             }
-            if (!p.b_mn) {
+            if (skip_b) {
+            } else if (!p.b_mn) {
               tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
             } else {
 #pragma unroll
@@ -304,6 +309,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint64_t bdesc0 = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
+            if (p.dbg & 4) break;
             umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc,
                       (kb > kb0 || k > 0) ? 1u : 0u);
           }
@@ -493,9 +499,31 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
   return m;
 }
 
+// Split-K factor for a persistent grid of `sms` CTAs walking equal-length tiles round-robin: minimise
+// waves x (k-blocks per slice + per-tile overhead).  A plain ceil(sms / tiles) overshoots the machine by a few tiles
+// and pays a whole second wave for them (conv2 wgrad: 13 tiles x 12 slices = 156 > 148).
+static int choose_splits(int tiles, int num_kb, int sms) {
+  if (tiles >= sms || num_kb < 8) return 1;
+  const int kTileOverheadKb = 4;                    // pipeline fill + accumulator hand-off, in k-block units
+  int best = 1;
+  long long best_cost = -1;
+  const int max_s = std::min(num_kb / 4, 4 * sms);
+  for (int s = 1; s <= max_s; ++s) {
+    const int kb_per = (num_kb + s - 1) / s;
+    const int s_eff = (num_kb + kb_per - 1) / kb_per;
+    const long long waves = ((long long)tiles * s_eff + sms - 1) / sms;
+    const long long cost = waves * (kb_per + kTileOverheadKb) * 64 + s_eff;     // tie-break: fewer slices (less atomic traffic)
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s_eff; }
+  }
+  return best;
+}
+
+static int g_dbg = 0;
+
 template <int BN>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st) {
   using C = Cfg<BN>;
+  p.dbg = g_dbg;
   static bool attr_set = false;
   if (!attr_set) {
     check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
@@ -509,6 +537,8 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int 
 }
 
 }  // namespace gemm
+
+void gemm_set_debug(int flags) { gemm::g_dbg = flags; }
 
 // C[M,N] (ldc) = alpha * op(A) op(B) + bias, optional ReLU.
 //   a_mn == 0: A is [M, K] with row pitch lda (elements);  a_mn == 1: A is [K, M] with row pitch lda.
@@ -539,11 +569,7 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   const int num_kb = (K + BK - 1) / BK;
   int splits = 1;
   if (splitk > 1 && can_split) splits = splitk;
-  else if (splitk == 0 && can_split && mt * nt < sms && num_kb >= 8) {
-    splits = (sms + mt * nt - 1) / (mt * nt);
-    if (splits > num_kb / 4) splits = num_kb / 4;
-    if (splits < 1) splits = 1;
-  }
+  else if (splitk == 0 && can_split) splits = choose_splits(mt * nt, num_kb, sms);
   int kb_per = (num_kb + splits - 1) / splits;
   splits = (num_kb + kb_per - 1) / kb_per;          // every slice owns >= 1 k-block
 
@@ -670,13 +696,7 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
   p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + 63) / 64;
   p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / 64 - 1) / (BN / 64);
   p.num_kb = (int)((M + BK - 1) / BK);
-  int splits = 1;
-  const int tiles = p.mt * p.nt;
-  if (tiles < sms && p.num_kb >= 8) {
-    splits = (sms + tiles - 1) / tiles;
-    if (splits > p.num_kb / 4) splits = p.num_kb / 4;
-    if (splits < 1) splits = 1;
-  }
+  int splits = choose_splits(p.mt * p.nt, p.num_kb, sms);
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.splits = splits; p.atomic_out = splits > 1;

@@ -482,6 +482,100 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
   count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd"); ::tmpi::check_capture(st, "relu_bias_bwd");
 }
 
+// Fused backward of  conv(+bias+ReLU) -> max-pool : one pass over the conv output instead of three.
+//   dym[n,h,w,c] = (sum over pooling windows whose argmax is (h,w) of dyp) * (y[n,h,w,c] > 0)     (bf16, contiguous)
+//   db[c]       += sum_{n,h,w} dym                                                                 (pre-zeroed by the launcher)
+// Channels < c_split accumulate into db0, the rest into db1 (the two parameter sets of a 2-group AlexNet block).
+// Replaces maxpool_bwd (write dx) + relu_bias_bwd (read dx, read y, write dym): 2 reads + 2 writes of the big tensor -> 1 + 1.
+__global__ void maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+                                             const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dym,
+                                             float* __restrict__ db0, float* __restrict__ db1, int c_split, PoolGeom g,
+                                             int VT, int rows_per_cta) {
+  extern __shared__ float sm[];                       // [RL][VT*8]
+  const int nvec = g.C >> 3;
+  const int RL = blockDim.x / VT;
+  const int tv = threadIdx.x % VT, tr = threadIdx.x / VT;
+  const int cv = blockIdx.y * VT + tv;
+  const long long R = (long long)g.N * g.H * g.W;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  float tot[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot[i] = 0.f;
+  if (tr < RL && cv < nvec) {
+    for (long long r = r0 + tr; r < min(R, r0 + rows_per_cta); r += RL) {
+      const int w = (int)(r % g.W); const long long t = r / g.W;
+      const int h = (int)(t % g.H); const int n = (int)(t / g.H);
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      int ho_lo = (h + g.p - g.k + g.s) / g.s; if (h + g.p - g.k + 1 <= 0) ho_lo = 0;
+      int wo_lo = (w + g.p - g.k + g.s) / g.s; if (w + g.p - g.k + 1 <= 0) wo_lo = 0;
+      const int ho_hi = min(g.Ho - 1, (h + g.p) / g.s);
+      const int wo_hi = min(g.Wo - 1, (w + g.p) / g.s);
+      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        const int kh = h + g.p - ho * g.s;
+        if (kh < 0 || kh >= g.k) continue;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          const int kw = w + g.p - wo * g.s;
+          if (kw < 0 || kw >= g.k) continue;
+          const long long o = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8;
+          const uint2 a = *reinterpret_cast<const uint2*>(arg + o);
+          float d[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(dyp + o), d);
+          const uint32_t me = (uint32_t)(kh * g.k + kw);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t ai = ((i < 4 ? a.x : a.y) >> (8 * (i & 3))) & 0xFFu;
+            if (ai == me) acc[i] += d[i];
+          }
+        }
+      }
+      float v[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(y + r * g.C + cv * 8), v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) acc[i] = 0.f;
+      const bf16x8 pk = pack8(acc);
+      *reinterpret_cast<bf16x8*>(dym + r * g.C + cv * 8) = pk;
+      unpack8(pk, acc);                                 // db sums what wgrad / dgrad will actually see (bf16-rounded)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tot[i] += acc[i];
+    }
+  }
+  if (tr < RL) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sm[(tr * VT + tv) * 8 + i] = tot[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < VT * 8) {
+    const int v = threadIdx.x / 8, i = threadIdx.x % 8;
+    const int c = (blockIdx.y * VT + v) * 8 + i;
+    if (c < g.C) {
+      float sacc = 0.f;
+      for (int t = 0; t < RL; ++t) sacc += sm[(t * VT + v) * 8 + i];
+      atomicAdd(c < c_split ? db0 + c : db1 + (c - c_split), sacc);
+    }
+  }
+}
+
+void maxpool_relu_bias_bwd(const void* dyp, const void* arg, const void* y, void* dym, void* db0, void* db1, int c_split, int N, int H,
+                           int W, int C, int Ho, int Wo, int k, int s, int p, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("maxpool_relu_bias_bwd: C must be a multiple of 8");
+  PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
+  const int nvec = C / 8;
+  const int VT = nvec < 32 ? nvec : 32;
+  const int RL = 256 / VT;
+  const int rows_per_cta = RL * 8;
+  const long long R = (long long)N * H * W;
+  dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
+  const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
+  if (c_split > C) c_split = C;
+  check_cuda(cudaMemsetAsync(db0, 0, (size_t)c_split * 4, st), "maxpool_relu_bias_bwd memset");
+  if (c_split < C) check_cuda(cudaMemsetAsync(db1, 0, (size_t)(C - c_split) * 4, st), "maxpool_relu_bias_bwd memset");
+  maxpool_relu_bias_bwd_kernel<<<grid, 256, smem, st>>>((const __nv_bfloat16*)dyp, (const uint8_t*)arg, (const __nv_bfloat16*)y,
+                                                         (__nv_bfloat16*)dym, (float*)db0, (float*)db1, c_split, g, VT, rows_per_cta);
+  count_launch(); TMPI_CHECK_LAUNCH("maxpool_relu_bias_bwd"); ::tmpi::check_capture(st, "maxpool_relu_bias_bwd");
+}
+
 // ============================================================================ im2col / col2im (NHWC, bf16)
 struct ConvGeom { int N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p; long long ldcol; int K; };
 

@@ -389,14 +389,16 @@ class ConvPoolLRN(Layer):
         return (B, h, w, cout)
 
     def forward(self, x):
+        # the pooling layer runs inside the conv's autograd node: its backward is one fused kernel
+        # (pool scatter + ReLU mask + bias gradient) instead of three passes over the conv output
+        pool = None
+        if self.poolsize != 1:
+            pool = (self.poolsize, self.poolstride, self.poolpad, "max" if self.mode == "max" else "avg")
         if self.group == 1:
-            y = ops.conv2d_bias_act(x, self.W.val, self.b.val, self.convstride, self.padsize, 1, True)
+            y = ops.conv2d_bias_act(x, self.W.val, self.b.val, self.convstride, self.padsize, 1, True, pool)
         else:
             y = ops.conv2d_group2_bias_act(x, self.W0.val, self.b0.val, self.W1.val, self.b1.val,
-                                           self.convstride, self.padsize, True)
-        if self.poolsize != 1:
-            y = ops.pool2d(y, self.poolsize, self.poolstride, self.poolpad,
-                           "max" if self.mode == "max" else "avg")
+                                           self.convstride, self.padsize, True, pool)
         if self.lrn:
             y = self.lrn_func(y)
         return y

@@ -110,6 +110,20 @@ def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld):
     return dym, db
 
 
+def maxpool_relu_bias_bwd(dyp, arg, y, pool, db0, db1=None):
+    """Backward of conv(+ReLU)→max-pool up to the conv's masked output gradient, in one kernel: scatter the pooled
+    gradient through the argmax, apply the ReLU mask, accumulate the bias gradient(s).  Returns dym, shaped like y."""
+    dyp = _bf(dyp).contiguous()
+    N, H, W, C = y.shape
+    Ho, Wo = dyp.shape[1], dyp.shape[2]
+    k, s_, p_ = int(pool[0]), int(pool[1]), int(pool[2])
+    dym = torch.empty((N, H, W, C), dtype=BF16, device=y.device)
+    c_split = C if db1 is None else int(db0.numel())
+    L().maxpool_relu_bias_bwd(dyp.data_ptr(), arg.data_ptr(), y.data_ptr(), dym.data_ptr(), db0.data_ptr(), _p(db1), c_split,
+                              N, H, W, C, Ho, Wo, k, s_, p_, _st(y))
+    return dym
+
+
 def linear_bias_act_bwd(x, w, y, dy, relu, need_dx, dw_out=None, db_out=None):
     x2 = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
@@ -238,13 +252,16 @@ def _conv_s2d_fwd(x, w, b, relu, g):
     return y, xs
 
 
-def _conv_s2d_bwd(xs, w, y, dy, relu, g, dw_out, db_out):
+def _conv_s2d_bwd(xs, w, y, dy, relu, g, dw_out, db_out, pre_masked=False):
     S, Hs, Ws, KHs, KWs, Cp, Ho, Wo = g
     O, KH, KW, C = w.shape
     N = xs.shape[0]
     M = N * Ho * Wo
     dev = xs.device
-    dym, db = _mask_and_bias_grad(dy.view(M, O), y.view(M, O), relu, db_out.view(-1) if db_out is not None else None, M, O, O)
+    if pre_masked:
+        dym, db = dy, db_out
+    else:
+        dym, db = _mask_and_bias_grad(dy.view(M, O), y.view(M, O), relu, db_out.view(-1) if db_out is not None else None, M, O, O)
     dws = torch.empty((O, KHs, KWs, Cp), dtype=torch.float32, device=dev)
     L().conv_wgrad(dym.data_ptr(), xs.data_ptr(), dws.data_ptr(), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O, _st(xs))
     dw = dw_out if dw_out is not None else torch.empty((O, KH, KW, C), dtype=torch.float32, device=dev)
@@ -282,7 +299,7 @@ def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu, return_cols=Fal
     return (y, cols) if return_cols else y
 
 
-def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out, col=None):
+def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out, col=None, pre_masked=False):
     N, H, W, Ct = x.shape
     Og, KH, KW, _ = w.shape
     Ho, Wo, Ot = y.shape[1], y.shape[2], y.shape[3]
@@ -290,42 +307,48 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
     dev = x.device
     dyv = dy.view(M, Ot)[:, o_off:o_off + Og]
     yv = y.view(M, Ot)[:, o_off:o_off + Og]
-    dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
+    if pre_masked:
+        # dy already carries the ReLU mask and db is already accumulated (fused pool backward): the GEMMs read this
+        # group's channel slice of the full tensor in place (row pitch Ot)
+        dym, db, ldy, dy_coff = dyv, db_out, Ot, o_off
+    else:
+        dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
+        ldy, dy_coff = Og, 0
     wb = _bf(w)
     if col is None and _implicit_ok(x, wb, c_off, Cg, Ot, o_off):
         # ---- implicit GEMM backward: wgrad gathers im2col(x) by TMA; dgrad (stride 1) is a forward conv of dy with the
         # flipped / transposed filter, written straight into dx's channel slice.
         dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
         L().conv_wgrad(dym.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
-                       Og, Og, _st(x))
+                       Og, int(ldy), _st(x))
         if need_dx:
             if s == 1:
                 wt = torch.empty((Cg, KH, KW, Og), dtype=BF16, device=dev)
                 L().conv_weight_flip(wb.data_ptr(), wt.data_ptr(), Og, KH, KW, int(Cg), _st(x))
-                L().conv_fprop(dym.data_ptr(), wt.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, Og, 0, Og, KH, KW, H, W, 1,
-                               KH - 1 - int(p), int(Cg), Ct, 0, 1, _st(x))
+                L().conv_fprop(dym.data_ptr() - dy_coff * 2, wt.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, int(ldy), int(dy_coff),
+                               Og, KH, KW, H, W, 1, KH - 1 - int(p), int(Cg), Ct, 0, 1, _st(x))
             else:
                 colK = KH * KW * Cg
                 Kp = (colK + 7) // 8 * 8
-                dcol = gemm(dym, _w2d(w, colK, Kp), M, Kp, Og, b_mn=True, lda=Og, ldb=Kp)
+                dcol = gemm(dym, _w2d(w, colK, Kp), M, Kp, Og, b_mn=True, lda=ldy, ldb=Kp)
                 L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
         return dw, db
     col, Kp, K = col if col is not None else _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)   # forward's matrix is reused
     dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
     # wgrad: dW[Og, K] = dymᵀ[Og, M] · col[M, K]   (both operands MN-major, split-K over M)
-    gemm(dym, col, Og, K, M, a_mn=True, b_mn=True, out=dw.view(Og, K), lda=Og, ldb=Kp, ldc=K)
+    gemm(dym, col, Og, K, M, a_mn=True, b_mn=True, out=dw.view(Og, K), lda=ldy, ldb=Kp, ldc=K)
     if need_dx:
         w2 = _w2d(w, K, Kp)
         one_by_one = (KH == 1 and KW == 1 and s == 1 and p == 0 and c_off == 0 and Cg == Ct)
         if one_by_one:
-            gemm(dym, w2, M, Kp, Og, b_mn=True, out=dx.view(M, Ct), lda=Og, ldb=Kp, ldc=Ct)
+            gemm(dym, w2, M, Kp, Og, b_mn=True, out=dx.view(M, Ct), lda=ldy, ldb=Kp, ldc=Ct)
         else:
-            dcol = gemm(dym, w2, M, Kp, Og, b_mn=True, lda=Og, ldb=Kp)
+            dcol = gemm(dym, w2, M, Kp, Og, b_mn=True, lda=ldy, ldb=Kp)
             L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
     return dw, db
 
 
-def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None, cols=None):
+def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None, cols=None, pre_masked=False):
     x = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
     N, H, W, C = x.shape
@@ -333,7 +356,7 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
     if cols and isinstance(cols[0], tuple) and len(cols[0]) == 3 and isinstance(cols[0][0], str) and cols[0][0] == "s2d":
         if need_dx:
             raise RuntimeError("space-to-depth conv path is for the first layer only (no input gradient)")
-        dw, db = _conv_s2d_bwd(cols[0][1], w, y, dy, relu, cols[0][2], dw_out, db_out)
+        dw, db = _conv_s2d_bwd(cols[0][1], w, y, dy, relu, cols[0][2], dw_out, db_out, pre_masked)
         return None, dw, db
     if (Cg % 8 or O % 8) and need_dx:
         raise RuntimeError("conv dgrad needs channel counts that are multiples of 8")
@@ -341,25 +364,26 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
     Og = O // groups
     if groups == 1:
         dw, db = _conv_bwd_group(x, w, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, dw_out, db_out,
-                                 col=cols[0] if cols else None)
+                                 col=cols[0] if cols else None, pre_masked=pre_masked)
         return dx, dw, db
     dw = dw_out if dw_out is not None else torch.empty(tuple(w.shape), dtype=torch.float32, device=x.device)
     db = db_out if db_out is not None else torch.empty(O, dtype=torch.float32, device=x.device)
     for g in range(groups):
         _conv_bwd_group(x, w[g * Og:(g + 1) * Og], y, dy, dx, g * Og, g * Cg, Cg, stride, pad, relu, need_dx,
-                        dw[g * Og:(g + 1) * Og], db[g * Og:(g + 1) * Og], col=cols[g] if cols else None)
+                        dw[g * Og:(g + 1) * Og], db[g * Og:(g + 1) * Og], col=cols[g] if cols else None, pre_masked=pre_masked)
     return dx, dw, db
 
 
-def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, outs=(None, None, None, None), cols=None):
+def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, outs=(None, None, None, None), cols=None,
+                               pre_masked=False):
     x = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
     Og, KH, KW, Cg = w0.shape
     dx = torch.empty_like(x) if need_dx else None
     dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1],
-                               col=cols[0] if cols else None)
+                               col=cols[0] if cols else None, pre_masked=pre_masked)
     dw1, db1 = _conv_bwd_group(x, w1, y, dy, dx, Og, Cg, Cg, stride, pad, relu, need_dx, outs[2], outs[3],
-                               col=cols[1] if cols else None)
+                               col=cols[1] if cols else None, pre_masked=pre_masked)
     return dx, (dw0, db0, dw1, db1)
 
 

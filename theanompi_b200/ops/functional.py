@@ -94,9 +94,21 @@ def linear_bias_act(x, w, b, relu=True):
 
 
 # --------------------------------------------------------------------------- conv
+def _fused_pool_ok(x, relu, pool):
+    """conv(+ReLU) → max-pool blocks run their backward through ONE fused kernel (pool scatter + ReLU mask + bias grad)."""
+    return pool is not None and x.is_cuda and relu and pool[3] == "max"
+
+
+def _pool_fwd_after(ctx, impl, y, pool):
+    """Forward of the pooling half of a fused conv→pool block; returns (pooled, argmax or None)."""
+    if impl is ref:
+        return ref.pool2d(y, pool[0], pool[1], pool[2], pool[3]), None
+    return impl.pool2d_fwd(y, pool[0], pool[1], pool[2], pool[3])
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, b, stride, pad, groups, relu):
+    def forward(ctx, x, w, b, stride, pad, groups, relu, pool=None):
         impl = _impl(x)
         wc = compute_weight(w)
         ctx.cols = None
@@ -108,32 +120,56 @@ class _ConvFn(torch.autograd.Function):
             y, ctx.cols = impl.conv2d_bias_act(x, wc, b, stride, pad, groups, relu, return_cols=True)
             if not CACHE_COL:
                 ctx.cols = None
-        ctx.save_for_backward(x, y)
         ctx.w, ctx.b = w, b
         ctx.cfg = (stride, pad, groups, relu)
-        return y
+        ctx.pool = pool
+        if pool is None:
+            ctx.save_for_backward(x, y)
+            return y
+        yp, arg = _pool_fwd_after(ctx, impl, y, pool)
+        ctx.has_arg = arg is not None
+        if arg is not None:
+            ctx.save_for_backward(x, y, arg)
+        else:
+            ctx.save_for_backward(x, y, yp)
+        return yp
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
+        x, y = ctx.saved_tensors[0], ctx.saved_tensors[1]
         w, b = ctx.w, ctx.b
         stride, pad, groups, relu = ctx.cfg
+        pool = ctx.pool
         impl = _impl(x)
         wc = compute_weight(w)
         need_dx = ctx.needs_input_grad[0]
         if impl is ref:
+            if pool is not None:
+                dy = ref.pool2d_bwd(y, ctx.saved_tensors[2], dy.contiguous(), *pool)
             dx, dw, db = ref.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx)
         else:
+            pre = False
+            db_out = _gout(b)
+            if pool is not None:
+                if _fused_pool_ok(x, relu, pool) and ctx.has_arg:
+                    if db_out is None:
+                        db_out = torch.empty(b.numel(), dtype=torch.float32, device=x.device)
+                    dy = impl.maxpool_relu_bias_bwd(dy, ctx.saved_tensors[2], y, pool, db_out, None)
+                    pre = True
+                else:
+                    dy = impl.pool2d_bwd_arg(dy, ctx.saved_tensors[2] if ctx.has_arg else None, tuple(y.shape), *pool)
             dx, dw, db = impl.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx,
-                                                  dw_out=_gout(w), db_out=_gout(b), cols=ctx.cols)
+                                                  dw_out=_gout(w), db_out=db_out, cols=ctx.cols, pre_masked=pre)
             ctx.cols = None
         gb = _sink(b, db)
         gw = _sink(w, dw)
-        return dx, gw, gb, None, None, None, None
+        return dx, gw, gb, None, None, None, None, None
 
 
-def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True):
-    return _ConvFn.apply(x, w, b, stride, pad, groups, relu)
+def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True, pool=None):
+    """``pool`` = (ksize, stride, pad, mode): run the pooling layer that follows inside the same autograd node, so the
+    backward can fuse pool-scatter + ReLU mask + bias gradient into one pass over the conv output."""
+    return _ConvFn.apply(x, w, b, stride, pad, groups, relu, pool)
 
 
 class _ConvG2Fn(torch.autograd.Function):
@@ -143,7 +179,7 @@ class _ConvG2Fn(torch.autograd.Function):
     offset and the GEMM epilogue writes each half of the output with ldc = C_out."""
 
     @staticmethod
-    def forward(ctx, x, w0, b0, w1, b1, stride, pad, relu):
+    def forward(ctx, x, w0, b0, w1, b1, stride, pad, relu, pool=None):
         impl = _impl(x)
         ws = [compute_weight(w0), compute_weight(w1)]
         if impl is ref:
@@ -156,19 +192,31 @@ class _ConvG2Fn(torch.autograd.Function):
             y, ctx.cols = impl.conv2d_group2_bias_act(x, ws[0], b0, ws[1], b1, stride, pad, relu, return_cols=True)
             if not CACHE_COL:
                 ctx.cols = None
-        ctx.save_for_backward(x, y)
         ctx.p = (w0, b0, w1, b1)
         ctx.cfg = (stride, pad, relu)
-        return y
+        ctx.pool = pool
+        if pool is None:
+            ctx.save_for_backward(x, y)
+            return y
+        yp, arg = _pool_fwd_after(ctx, impl, y, pool)
+        ctx.has_arg = arg is not None
+        if arg is not None:
+            ctx.save_for_backward(x, y, arg)
+        else:
+            ctx.save_for_backward(x, y, yp)
+        return yp
 
     @staticmethod
     def backward(ctx, dy):
-        x, y = ctx.saved_tensors
+        x, y = ctx.saved_tensors[0], ctx.saved_tensors[1]
         w0, b0, w1, b1 = ctx.p
         stride, pad, relu = ctx.cfg
+        pool = ctx.pool
         impl = _impl(x)
         need_dx = ctx.needs_input_grad[0]
         if impl is ref:
+            if pool is not None:
+                dy = ref.pool2d_bwd(y, ctx.saved_tensors[2], dy.contiguous(), *pool)
             C, O = x.shape[-1], y.shape[-1]
             outs = []
             for g, (w, b) in enumerate(((w0, b0), (w1, b1))):
@@ -180,19 +228,31 @@ class _ConvG2Fn(torch.autograd.Function):
             dx = torch.cat([outs[0][0], outs[1][0]], dim=-1) if need_dx else None
             grads = (outs[0][1], outs[0][2], outs[1][1], outs[1][2])
         else:
+            pre = False
+            db0, db1 = _gout(b0), _gout(b1)
+            if pool is not None:
+                if _fused_pool_ok(x, relu, pool) and ctx.has_arg:
+                    if db0 is None:
+                        db0 = torch.empty(b0.numel(), dtype=torch.float32, device=x.device)
+                    if db1 is None:
+                        db1 = torch.empty(b1.numel(), dtype=torch.float32, device=x.device)
+                    dy = impl.maxpool_relu_bias_bwd(dy, ctx.saved_tensors[2], y, pool, db0, db1)
+                    pre = True
+                else:
+                    dy = impl.pool2d_bwd_arg(dy, ctx.saved_tensors[2] if ctx.has_arg else None, tuple(y.shape), *pool)
             dx, grads = impl.conv2d_group2_bias_act_bwd(
                 x, compute_weight(w0), compute_weight(w1), y, dy, stride, pad, relu, need_dx,
-                outs=(_gout(w0), _gout(b0), _gout(w1), _gout(b1)), cols=ctx.cols)
+                outs=(_gout(w0), db0, _gout(w1), db1), cols=ctx.cols, pre_masked=pre)
             ctx.cols = None
         gb1 = _sink(b1, grads[3])
         gw1 = _sink(w1, grads[2])
         gb0 = _sink(b0, grads[1])
         gw0 = _sink(w0, grads[0])
-        return dx, gw0, gb0, gw1, gb1, None, None, None
+        return dx, gw0, gb0, gw1, gb1, None, None, None, None
 
 
-def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride=1, pad=0, relu=True):
-    return _ConvG2Fn.apply(x, w0, b0, w1, b1, stride, pad, relu)
+def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride=1, pad=0, relu=True, pool=None):
+    return _ConvG2Fn.apply(x, w0, b0, w1, b1, stride, pad, relu, pool)
 
 
 # --------------------------------------------------------------------------- pool

@@ -63,6 +63,7 @@ struct Params {
   int conv_mode;
   int cHo, cWo, cS, cP, cKH, cKW, cCg, c_chunks;
   int atomic_out;       // 1 = fp32 atomicAdd (split-K)
+  int group_m;          // tile raster: m-tiles per band (0 = plain m-fastest order); see tile_mn()
   int dbg;              // bottleneck probe (scripts/gemm_probe.py): 1 = skip A loads, 2 = skip B loads, 4 = skip the MMAs
 };
 
@@ -87,13 +88,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.  The spin loop lives INSIDE the asm
+// statement so the compiler sees straight-line code: a C++ loop around try_wait has a per-thread exit condition, which
+// makes everything after it "potentially divergent" and pushes the producer / MMA loop indices out of the uniform
+// registers (R2UR before every UTMALDG / UTCHMMA operand).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { __trap(); }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1, P2;\n\t"
+      ".reg .u32 cnt;\n\t"
+      "mov.u32 cnt, 0;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "add.u32 cnt, cnt, 1;\n\t"
+      "setp.lt.u32 P2, cnt, 0x1000000;\n\t"
+      "@P2 bra LAB_WAIT;\n\t"
+      "trap;\n\t"
+      "DONE:\n\t"
+      "}"
+      ::"r"(bar), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -122,6 +136,17 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// one lane of a fully converged warp (elect.sync): the issuing thread of the TMA / MMA warps
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -163,6 +188,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
   d |= (uint64_t)2 << 61;                                 // layout type: SWIZZLE_128B
   return d;
+}
+
+// Tile raster.  Default: m fastest (all CTAs of a wave share the few B tiles — right for conv / FC where one operand is
+// small).  For GEMMs with many tiles in both directions the wave is folded into bands of group_m m-tiles so the tiles that
+// run concurrently form a near-square block and re-use both operands out of L2 instead of streaming one from HBM.
+__device__ __forceinline__ void tile_mn(const Params& p, int rem, int& mti, int& nti) {
+  if (p.group_m <= 0) { nti = rem / p.mt; mti = rem - nti * p.mt; return; }
+  const int band_sz = p.group_m * p.nt;
+  const int band = rem / band_sz, within = rem - band * band_sz;
+  const int rows = min(p.group_m, p.mt - band * p.group_m);
+  nti = within / rows; mti = band * p.group_m + (within - nti * rows);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -208,71 +244,103 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      const bool skip_a = (p.dbg & 1) != 0, skip_b = (p.dbg & 2) != 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn, rem = tile % tiles_mn;
-        const int m0 = (rem % p.mt) * BM, n0 = (rem / p.mt) * BN;
-        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        // conv fprop/dgrad: decode the tile's first output pixel once
-        int img0 = 0, bw0 = 0, bh0 = 0;
-        if (p.conv_mode == 1) {
-          const int hw = p.cHo * p.cWo;
-          img0 = m0 / hw; const int r_ = m0 - img0 * hw; const int p0 = r_ / p.cWo, q0 = r_ - p0 * p.cWo;
-          bw0 = q0 * p.cS - p.cP; bh0 = p0 * p.cS - p.cP;
+    // The WHOLE warp walks the loops (so every index stays warp-uniform and lives in uniform registers — a loop body that
+    // sits inside `if (lane == 0)` is compiled with per-thread registers plus an R2UR/ELECT dance in front of every
+    // UTMALDG and cost ~450 cycles per k-block, more than the MMAs it feeds); one elected lane issues.  All per-k-block
+    // index math is incremental: no divisions inside the k loop.
+    const bool leader = elect_one();
+    const bool skip_a = (p.dbg & 1) != 0, skip_b = (p.dbg & 2) != 0;
+    const bool issue_a = leader && !skip_a, issue_b = leader && !skip_b;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int split = tile / tiles_mn, rem = tile - split * tiles_mn;
+      int mti, nti;
+      tile_mn(p, rem, mti, nti);
+      const int m0 = mti * BM, n0 = nti * BN;
+      const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      if (p.conv_mode == 1) {
+        // ---- conv fprop / dgrad: A = im2col box [128 pixels x 64 ch] of filter tap (r_, s_), channel chunk cc; B = weights
+        const int hw = p.cHo * p.cWo;
+        const int img0 = m0 / hw; const int r0_ = m0 - img0 * hw; const int p0 = r0_ / p.cWo, q0 = r0_ - p0 * p.cWo;
+        const int bw0 = q0 * p.cS - p.cP, bh0 = p0 * p.cS - p.cP;
+        int tap = kb0 / p.c_chunks, cc = kb0 - tap * p.c_chunks;
+        int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)C::A_BYTES) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_expect_tx(fb, tx);
+          if (issue_a) tma_load_im2col(sa, &tmap_a, fb, cc * BK, bw0, bh0, img0, s_, r_);
+          if (issue_b) tma_load_3d(sa + C::A_BYTES, &tmap_b, fb, cc * BK, tap, n0);
+          if (++cc == p.c_chunks) { cc = 0; ++tap; if (++s_ == p.cKW) { s_ = 0; ++r_; } }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        int w_box0 = 0;
-        if (p.conv_mode == 2) w_box0 = (rem / p.mt) * (BN >= 64 ? BN / 64 : 1);    // n-tile = BN/64 consecutive (tap, 64-channel) boxes
+      } else if (p.conv_mode == 2) {
+        // ---- conv wgrad: A = dy (MN-major) [64 m x 64 pixels] x2;  B = BN/64 im2col boxes [64 pixels x 64 ch], one per
+        //      (filter tap, channel chunk); the k loop walks pixels 64 at a time (W, then H, then N)
+        constexpr int NBOX = (BN >= 64) ? BN / 64 : 1;
+        const int total_boxes = p.cKH * p.cKW * p.c_chunks;
+        const int w_box0 = nti * NBOX;
+        int bc[NBOX], bs[NBOX], br[NBOX];
+        int nbox = 0;
+#pragma unroll
+        for (int j = 0; j < NBOX; ++j) {
+          const int box = w_box0 + j;
+          const int tapj = box / p.c_chunks, c64 = box - tapj * p.c_chunks;
+          br[j] = tapj / p.cKW; bs[j] = tapj - br[j] * p.cKW; bc[j] = c64 * 64;
+          if (box < total_boxes) ++nbox;
+        }
+        if (skip_b) nbox = 0;
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)C::A_BYTES) + (uint32_t)(nbox * (BK * 128));
+        const int hw = p.cHo * p.cWo;
+        int pix = kb0 * BK;
+        int img = pix / hw; const int r2 = pix - img * hw; int pp = r2 / p.cWo, qq = r2 - pp * p.cWo;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t sb = sa + C::A_BYTES;
-          if (p.conv_mode == 1) {
-            const int tap = kb / p.c_chunks, cc = kb - tap * p.c_chunks;
-            const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
-            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES));
-            if (!skip_a) tma_load_im2col(sa, &tmap_a, full_bar(stage), cc * BK, bw0, bh0, img0, s_, r_);      // [128 pixels x 64 ch]
-            if (!skip_b) tma_load_3d(sb, &tmap_b, full_bar(stage), cc * BK, tap, n0);                          // [BN out-ch x 64 ch]
-          } else if (p.conv_mode == 2) {
-            const int hw = p.cHo * p.cWo;
-            const int pix = kb * BK;
-            const int img = pix / hw; const int r2 = pix - img * hw; const int pp = r2 / p.cWo, qq = r2 - pp * p.cWo;
-            const int total_boxes = p.cKH * p.cKW * p.c_chunks;
-            int nbox = 0;
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_expect_tx(fb, tx);
+          if (issue_a) {
 #pragma unroll
-            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) if (w_box0 + j < total_boxes) ++nbox;
-            if (skip_b) nbox = 0;
-            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + nbox * (BK * 128));
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, fb, m0 + 64 * j, pix);
+          }
+          if (issue_b) {
+            const int cw = qq * p.cS - p.cP, ch = pp * p.cS - p.cP;
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)                                        // dy, MN-major: box {64 m, 64 pixels}
-              if (!skip_a) tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, pix);
-#pragma unroll
-            for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) {
-              const int box = w_box0 + j;
-              if (box < total_boxes && !skip_b) {                                     // [64 pixels x 64 ch] of one filter tap
-                const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
-                const int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
-                tma_load_im2col(sb + j * (BK * 128), &tmap_b, full_bar(stage), c64 * 64, qq * p.cS - p.cP, pp * p.cS - p.cP, img, s_, r_);
-              }
-            }
-          } else {
-            mbar_expect_tx(full_bar(stage), (skip_a ? 0 : C::A_BYTES) + (skip_b ? 0 : C::B_BYTES));
-            if (skip_a) {
-            } else if (!p.a_mn) {
-              tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BK, m0);                 // box {64 k, BM rows}
+            for (int j = 0; j < NBOX; ++j)
+              if (j < nbox) tma_load_im2col(sb + j * (BK * 128), &tmap_b, fb, bc[j], cw, ch, img, bs[j], br[j]);
+          }
+          pix += BK; qq += BK;
+          while (qq >= p.cWo) { qq -= p.cWo; if (++pp == p.cHo) { pp = 0; ++img; } }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+        }
+      } else {
+        // ---- plain GEMM: K-major operands are one box {64 k, rows}; MN-major operands are 64-wide column boxes {64 mn, 64 k}
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)C::A_BYTES) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
+        int k0 = kb0 * BK;
+        for (int kb = kb0; kb < kb1; ++kb, k0 += BK) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_expect_tx(fb, tx);
+          if (issue_a) {
+            if (!a_mn) {
+              tma_load_2d(sa, &tmap_a, fb, k0, m0);
             } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j)                                        // box {64 m, 64 k-rows}
-                tma_load_2d(sa + j * (BK * 128), &tmap_a, full_bar(stage), m0 + 64 * j, kb * BK);
+              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, fb, m0 + 64 * j, k0);
             }
-            if (skip_b) {
-            } else if (!p.b_mn) {
-              tma_load_2d(sb, &tmap_b, full_bar(stage), kb * BK, n0);
+          }
+          if (issue_b) {
+            if (!b_mn) {
+              tma_load_2d(sb, &tmap_b, fb, k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-                tma_load_2d(sb + j * (BK * 128), &tmap_b, full_bar(stage), n0 + 64 * j, kb * BK);
+              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, fb, n0 + 64 * j, k0);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -281,45 +349,49 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     __syncwarp();
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      // K-major, SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the 128 B row.
-      // MN-major, SW128: 64-element MN atoms BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
-      //                  advance 16 k-rows = 2048 B per UMMA_K.
-      const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_sbo = 1024u, a_step = p.a_mn ? 128u : 2u;
-      const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_sbo = 1024u, b_step = p.b_mn ? 128u : 2u;
-      int stage = 0; uint32_t phase = 0;
-      int t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-        const int split = tile / tiles_mn;
-        const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
-        const int acc = t & 1;
-        mbar_wait(tmem_empty_bar(acc), (uint32_t)(((t >> 1) & 1) ^ 1));       // epilogue drained this accumulator
+    // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
+    const bool leader = elect_one();
+    const bool skip_mma = (p.dbg & 4) != 0;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+                           ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    // K-major, SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the 128 B row.
+    // MN-major, SW128: 64-element MN atoms BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+    //                  advance 16 k-rows = 2048 B per UMMA_K.
+    const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_step = p.a_mn ? 128u : 2u;
+    const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_step = p.b_mn ? 128u : 2u;
+    const uint64_t adesc_base = make_smem_desc(smem_base, a_lbo, 1024u);
+    const uint64_t bdesc_base = make_smem_desc(smem_base + C::A_BYTES, b_lbo, 1024u);
+    int stage = 0; uint32_t phase = 0;
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int split = tile / tiles_mn;
+      const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      const int acc = t & 1;
+      mbar_wait(tmem_empty_bar(acc), (uint32_t)(((t >> 1) & 1) ^ 1));       // epilogue drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      uint32_t accumulate = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sb = sa + C::A_BYTES;
-          const uint64_t adesc0 = make_smem_desc(sa, a_lbo, a_sbo);
-          const uint64_t bdesc0 = make_smem_desc(sb, b_lbo, b_sbo);
+        if (leader) {
+          const uint64_t adesc0 = adesc_base + (uint64_t)((uint32_t)(stage * C::STAGE_BYTES) >> 4);
+          const uint64_t bdesc0 = bdesc_base + (uint64_t)((uint32_t)(stage * C::STAGE_BYTES) >> 4);
+          if (!skip_mma) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            if (p.dbg & 4) break;
-            umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc,
-                      (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc, accumulate);
+              accumulate = 1u;
+            }
           }
           umma_commit(empty_bar(stage));             // frees the smem slot once these MMAs retire
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(tmem_full_bar(acc));             // accumulator complete → epilogue
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(tmem_full_bar(acc));   // accumulator complete → epilogue
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue: TMEM → registers → smem staging → global =====================
     // 8 warps: warp w reads TMEM lane quarter q = w % 4 (hardware rule) and the column half (w - 2) / 4 of the tile.
@@ -335,12 +407,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int rem = tile % tiles_mn;
-      const int m0 = (rem % p.mt) * BM;
-      int n0 = (rem / p.mt) * BN, n_end = p.N;       // global column of tile column cc is n0 + cc
+      int mti, nti;
+      tile_mn(p, rem, mti, nti);
+      const int m0 = mti * BM;
+      int n0 = nti * BN, n_end = p.N;                // global column of tile column cc is n0 + cc
       if (p.conv_mode == 2) {
         // wgrad: every 64-column box of the tile is one (filter tap, 64-channel chunk); this warp's columns [col0, col0+64)
         // are exactly one box, which lands at column tap*Cg + c64*64 of dW.
-        const int box = (rem / p.mt) * (BN >= 64 ? BN / 64 : 1) + col0 / 64;
+        const int box = nti * (BN >= 64 ? BN / 64 : 1) + col0 / 64;
         if (box < p.cKH * p.cKW * p.c_chunks) {
           const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
           n0 = tap * p.cCg + c64 * 64 - col0;
@@ -348,6 +422,19 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         } else {
           n0 = 0; n_end = 0;
         }
+      }
+      // per-column bias: lane j prefetches the bias of column (chunk base + j) BEFORE waiting for the accumulator (the load
+      // hides behind the main loop) and the chunk loop broadcasts it with shuffles.  (32 dependent __ldg per chunk in the
+      // loop cost ~7 us per tile: the compiler serialised them through two registers.)
+      const int m = m0 + row;
+      const bool m_ok = m < p.M;
+      float bias_m = 0.f;
+      if (p.bias_mode == 2 && m_ok) bias_m = __ldg(p.bias + m);
+      float bias_c0 = 0.f, bias_c1 = 0.f;
+      if (p.bias_mode == 1 && active) {
+        const int cb = n0 + col0 + lane;
+        if (cb < n_end) bias_c0 = __ldg(p.bias + cb);
+        if (COLS_PER_WARP > 32 && cb + 32 < n_end) bias_c1 = __ldg(p.bias + cb + 32);
       }
       const int acc = t & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
@@ -358,10 +445,6 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         continue;
       }
-      const int m = m0 + row;
-      const bool m_ok = m < p.M;
-      float bias_m = 0.f;
-      if (p.bias_mode == 2 && m_ok) bias_m = p.bias[m];
       // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores
       // (plain stores, or vector reductions red.global.add.v4.f32 for split-K).
       const bool staged = (n0 + col0 + COLS_PER_WARP <= n_end) && (((long long)p.ldc * esz) % 16 == 0) &&
@@ -380,16 +463,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         }
         const int nb = n0 + cc;
-        if (!staged && (!m_ok || nb >= n_end)) continue;
+        const float bias_sel = (c == 0) ? bias_c0 : bias_c1;
         float v[32];
+        if (p.bias_mode == 1) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * p.alpha;
-          if (p.bias_mode == 1) { x += (nb + j < n_end) ? __ldg(p.bias + nb + j) : 0.f; }
-          else if (p.bias_mode == 2) { x += bias_m; }
-          if (p.relu) x = fmaxf(x, 0.f);
-          v[j] = x;
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, __shfl_sync(0xffffffffu, bias_sel, j));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias_m);
         }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (!staged && (!m_ok || nb >= n_end)) continue;
         if (staged) {
           uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)cc * esz;
           if (p.out_bf16) {
@@ -577,6 +664,7 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
   p.mt = mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
+  p.group_m = (mt > 16 && nt > 16) ? 12 : 0;
   p.cHo = p.cWo = p.cS = p.cP = p.cKH = p.cKW = p.cCg = p.c_chunks = 0;
   if (splits > 1) {
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
@@ -674,6 +762,7 @@ void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, i
   p.C = y; p.bias = bias; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = 0;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? 1 : 0; p.relu = relu; p.atomic_out = 0;
   p.mt = (int)((M + BM - 1) / BM); p.nt = (O + BN - 1) / BN; p.splits = 1;
+  p.group_m = 0;
   p.conv_mode = 1; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BK - 1) / BK;
   p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
   CUtensorMap ta = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BM);
@@ -693,6 +782,7 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
   Params p;
   p.C = dw; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
   p.out_bf16 = 0; p.bias_mode = 0; p.relu = 0;
+  p.group_m = 0;
   p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + 63) / 64;
   p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / 64 - 1) / (BN / 64);
   p.num_kb = (int)((M + BK - 1) / BK);

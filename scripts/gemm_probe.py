@@ -50,7 +50,7 @@ def conv_case(name, N, H, W, C, O, K, s, p):
     flops = 2.0 * N * Ho * Ho * O * K * K * C
 
     def f():
-        L.conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), b.data_ptr(), N, H, W, C, 0, C, K, K, Ho, Ho, s, p, O, O, 1, 1, S())
+        L.conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), b.data_ptr(), N, H, W, C, 0, C, K, K, Ho, Ho, s, p, O, O, 1, 1, 0, S())
 
     def g():
         L.conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, C, 0, C, K, K, Ho, Ho, s, p, O, O, S())

@@ -55,6 +55,24 @@ def test_gemm_epilogue_bias_relu_bf16(bn):
     assert rel_err(out, want) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn", [(4096, 1024, 256, False, False), (4000, 520, 200, False, True),
+                                             (4232, 1024, 128, True, False), (4196, 640, 192, False, False)])
+def test_gemm_tall_tiles(M, N, K, a_mn, b_mn):
+    """bf16-output GEMMs with many rows run 256-row CTA tiles (two MMAs per k-step sharing the B tile); the last tile's
+    second half may be partial (4232, 4000) or entirely out of range (4196)."""
+    ci = _impl()
+    torch.manual_seed(21)
+    A = torch.randn((K, M) if a_mn else (M, K), device=DEV).to(torch.bfloat16)
+    B = torch.randn((K, N) if b_mn else (N, K), device=DEV).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV)
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float() if b_mn else B.float().t()
+    want = torch.relu(Af @ Bf + bias)
+    out = ci.gemm(A, B, M, N, K, a_mn=a_mn, b_mn=b_mn, bias=bias, bias_mode=1, relu=True, lda=A.shape[1], ldb=B.shape[1])
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 1e-2
+
+
 def test_gemm_splitk_and_strided_out():
     ci = _impl()
     torch.manual_seed(2)
@@ -96,6 +114,8 @@ def test_linear_fwd_bwd():
     dict(N=2, H=12, W=12, C=192, O=64, k=3, s=1, p=1),     # 3 channel chunks per tap
     dict(N=3, H=27, W=27, C=48, O=128, k=5, s=1, p=2),     # AlexNet conv2 group shape (C = 48)
     dict(N=40, H=13, W=13, C=256, O=384, k=3, s=1, p=1),   # many tiles + split-K wgrad
+    dict(N=32, H=27, W=27, C=48, O=128, k=5, s=1, p=2),    # enough pixels for 256-row tiles in fprop and dgrad (BN = 64)
+    dict(N=37, H=13, W=13, C=192, O=192, k=3, s=1, p=1),   # 256-row tiles with a ragged last tile
 ])
 def test_conv_fwd_bwd(cfg):
     torch.manual_seed(4)

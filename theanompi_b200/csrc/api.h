@@ -47,7 +47,7 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
                cudaStream_t st);
 
 void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
-                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, cudaStream_t st);
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st);
 void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
                      int Wo, int S, int P, int O, long long ldy, cudaStream_t st);
 

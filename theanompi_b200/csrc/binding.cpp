@@ -55,8 +55,9 @@ PYBIND11_MODULE(_tmpi_native, m) {
   });
 
   m.def("conv_fprop", [](ptr_t x, ptr_t w, ptr_t y, ptr_t bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo,
-                         int S, int Pd, int O, long long ldc, int relu, int out_bf16, ptr_t st) {
-    conv_fprop_bf16(P(x), P(w), P(y), (const float*)P(bias), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldc, relu, out_bf16, S_(st));
+                         int S, int Pd, int O, long long ldc, int relu, int out_bf16, int dgrad, ptr_t st) {
+    conv_fprop_bf16(P(x), P(w), P(y), (const float*)P(bias), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldc, relu, out_bf16, dgrad,
+                    S_(st));
   });
   m.def("conv_wgrad", [](ptr_t dy, ptr_t x, ptr_t dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int S,
                          int Pd, int O, long long ldy, ptr_t st) {

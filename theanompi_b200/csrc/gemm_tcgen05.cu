@@ -31,17 +31,26 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
 
-template <int BN> struct Cfg {
-  // persistent kernel, one CTA per SM: operand ring + a dedicated epilogue staging tile + 2 TMEM accumulators
-  static constexpr int STAGES = (BN == 128) ? 4 : (BN == 64 ? 6 : 8);
-  static constexpr int A_BYTES = BM * BK * 2;
+// MT = number of 128-row sub-tiles a CTA computes per k-block against ONE copy of the B tile (MT = 2: a 256 x BN tile as two
+// MMAs per k-step — half the B (weight) reads per flop, half the per-k-block barrier / issue overhead per flop).
+template <int BN, int MT> struct Cfg {
+  // persistent kernel, one CTA per SM: operand ring + per-warp epilogue staging chunks + 2 TMEM accumulator stages
+  static constexpr int A_BYTES = MT * BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_PITCH_MAX = BN * 4 + 16;                 // fp32 row + 16 B (conflict-free v4 stores)
-  static constexpr int STAGING_BYTES = BM * STAGING_PITCH_MAX;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // epilogue staging: each epilogue warp transposes one 32-row x 32-column chunk at a time through its own region
+  // (row pitch = chunk bytes + 16 B: conflict-free 16 B accesses).  MT = 2 tiles are bf16-output only (fprop / dgrad).
+  static constexpr int STAGING_ROW = (MT == 2 ? 32 * 2 : 32 * 4) + 16;
+  static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * STAGING_ROW;
+  static constexpr int SMEM_LIMIT = 232448;                                // 227 KB per CTA
+  static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 256 /*barriers*/;
+  static constexpr int STAGES = (RING_BUDGET / STAGE_BYTES) > 8 ? 8 : (RING_BUDGET / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
   static constexpr int ACC_STAGES = 2;
-  static constexpr int TMEM_COLS = (2 * BN < 32) ? 32 : 2 * BN;         // power of two >= 32 (64 / 128 / 256)
+  static constexpr int ACC_COLS = MT * BN;                                 // TMEM columns of one accumulator stage
+  static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : (2 * ACC_COLS <= 256 ? 256 : 512)));
+  static_assert(STAGES >= 3, "operand ring too shallow");
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
 struct Params {
@@ -207,10 +216,11 @@ __device__ __forceinline__ void tile_mn(const Params& p, int rem, int& mti, int&
 //   MMA thread → TMEM accumulator A/B (tmem_full/tmem_empty) → epilogue warps
 // so the epilogue of tile i overlaps the main loop of tile i+1 and all per-CTA setup (TMEM alloc, barrier init,
 // descriptor fetch) is paid once per SM instead of once per tile.
-template <int BN>
+template <int BN, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MT>;
+  constexpr int TM = MT * BM;                      // rows of a CTA tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024B alignment
   const uint32_t staging_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -256,23 +266,46 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int split = tile / tiles_mn, rem = tile - split * tiles_mn;
       int mti, nti;
       tile_mn(p, rem, mti, nti);
-      const int m0 = mti * BM, n0 = nti * BN;
+      const int m0 = mti * TM, n0 = nti * BN;
       const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
+      // sub-tiles that start beyond M are not loaded at all (their MMAs chew on stale smem; the epilogue drops the rows)
+      const int n_sub = (MT == 2 && m0 + BM < p.M) ? 2 : 1;
       if (p.conv_mode == 1) {
         // ---- conv fprop / dgrad: A = im2col box [128 pixels x 64 ch] of filter tap (r_, s_), channel chunk cc; B = weights
         const int hw = p.cHo * p.cWo;
-        const int img0 = m0 / hw; const int r0_ = m0 - img0 * hw; const int p0 = r0_ / p.cWo, q0 = r0_ - p0 * p.cWo;
-        const int bw0 = q0 * p.cS - p.cP, bh0 = p0 * p.cS - p.cP;
+        int img0[MT], bw0[MT], bh0[MT];
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+          const int mu = m0 + u * BM;
+          img0[u] = mu / hw; const int r0_ = mu - img0[u] * hw; const int p0 = r0_ / p.cWo, q0 = r0_ - p0 * p.cWo;
+          bw0[u] = q0 * p.cS - p.cP; bh0[u] = p0 * p.cS - p.cP;
+        }
         int tap = kb0 / p.c_chunks, cc = kb0 - tap * p.c_chunks;
         int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
-        const uint32_t tx = (skip_a ? 0u : (uint32_t)C::A_BYTES) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * BM * BK * 2)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const bool b_t = p.b_mn != 0;
+        const int ntaps = p.cKH * p.cKW;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
           const uint32_t fb = full_bar(stage);
           if (leader) mbar_expect_tx(fb, tx);
-          if (issue_a) tma_load_im2col(sa, &tmap_a, fb, cc * BK, bw0, bh0, img0, s_, r_);
-          if (issue_b) tma_load_3d(sa + C::A_BYTES, &tmap_b, fb, cc * BK, tap, n0);
+          if (issue_a) {
+#pragma unroll
+            for (int u = 0; u < MT; ++u)
+              if (u < n_sub) tma_load_im2col(sa + u * (BM * BK * 2), &tmap_a, fb, cc * BK, bw0[u], bh0[u], img0[u], s_, r_);
+          }
+          if (issue_b) {
+            if (!b_t) {
+              tma_load_3d(sa + C::A_BYTES, &tmap_b, fb, cc * BK, tap, n0);            // weights [n][tap][k]: K-major box
+            } else {
+              // dgrad reads the FORWARD filter [k = out-ch][tap][n = in-ch] in place: MN-major boxes {64 n, 1 tap, 64 k} of
+              // the mirrored tap (no flipped / transposed copy of the weights)
+#pragma unroll
+              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
+                tma_load_3d(sa + C::A_BYTES + j * (BK * 128), &tmap_b, fb, n0 + 64 * j, ntaps - 1 - tap, cc * BK);
+            }
+          }
           if (++cc == p.c_chunks) { cc = 0; ++tap; if (++s_ == p.cKW) { s_ = 0; ++r_; } }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -318,7 +351,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
       } else {
         // ---- plain GEMM: K-major operands are one box {64 k, rows}; MN-major operands are 64-wide column boxes {64 mn, 64 k}
-        const uint32_t tx = (skip_a ? 0u : (uint32_t)C::A_BYTES) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * BM * BK * 2)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
         const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
         int k0 = kb0 * BK;
         for (int kb = kb0; kb < kb1; ++kb, k0 += BK) {
@@ -328,11 +361,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t fb = full_bar(stage);
           if (leader) mbar_expect_tx(fb, tx);
           if (issue_a) {
-            if (!a_mn) {
-              tma_load_2d(sa, &tmap_a, fb, k0, m0);
-            } else {
 #pragma unroll
-              for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, fb, m0 + 64 * j, k0);
+            for (int u = 0; u < MT; ++u) {
+              if (u < n_sub) {
+                if (!a_mn) {
+                  tma_load_2d(sa + u * (BM * BK * 2), &tmap_a, fb, k0, m0 + u * BM);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + u * (BM * BK * 2) + j * (BK * 128), &tmap_a, fb, m0 + u * BM + 64 * j, k0);
+                }
+              }
             }
           }
           if (issue_b) {
@@ -370,7 +408,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int acc = t & 1;
       mbar_wait(tmem_empty_bar(acc), (uint32_t)(((t >> 1) & 1) ^ 1));       // epilogue drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * C::ACC_COLS);
       uint32_t accumulate = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar(stage), phase);
@@ -381,7 +419,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (!skip_mma) {
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              umma_bf16(tmem_acc, adesc0 + (uint64_t)(a_step * k), bdesc0 + (uint64_t)(b_step * k), idesc, accumulate);
+#pragma unroll
+              for (int u = 0; u < MT; ++u)             // the MT sub-tiles share the B descriptor
+                umma_bf16(tmem_acc + (uint32_t)(u * BN), adesc0 + (uint64_t)(u * ((BM * BK * 2) >> 4)) + (uint64_t)(a_step * k),
+                          bdesc0 + (uint64_t)(b_step * k), idesc, accumulate);
               accumulate = 1u;
             }
           }
@@ -393,23 +434,30 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       __syncwarp();
     }
   } else {
-    // ===================== epilogue: TMEM → registers → smem staging → global =====================
-    // 8 warps: warp w reads TMEM lane quarter q = w % 4 (hardware rule) and the column half (w - 2) / 4 of the tile.
+    // ===================== epilogue: TMEM → registers → (per-warp smem transpose) → global =====================
+    // 8 warps: warp w reads TMEM lane quarter q = w % 4 (hardware rule) and the column half (w - 2) / 4 of the tile, one
+    // 32-column chunk at a time: tcgen05.ld → bias / ReLU → the warp's staging region (thread = row) → read back with
+    // thread = 16-byte vector so every global store / red covers whole 64–128 B row segments.
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
     constexpr int COLS_PER_WARP = (BN >= 64) ? BN / 2 : BN;          // BN = 32: only the first four warps carry data
+    constexpr int NCHUNK = COLS_PER_WARP / 32;
     const bool active = (BN >= 64) || half == 0;
     const int col0 = (BN >= 64) ? half * COLS_PER_WARP : 0;
-    const int row = 32 * q + lane;                 // row inside the tile
+    const int row = 32 * q + lane;                 // row inside a 128-row sub-tile
     const int esz = p.out_bf16 ? 2 : 4;
-    const uint32_t pitch = (uint32_t)(BN * esz + 16);
-    uint8_t* stage_ptr = smem_raw + (staging_base - smem_u32(smem_raw));
+    const uint32_t pitch = (uint32_t)(32 * esz + 16);
+    uint8_t* wstage = smem_raw + (staging_base - smem_u32(smem_raw)) + (size_t)(warp - 2) * 32 * C::STAGING_ROW;
+    const int vec_per_row = (32 * esz) / 16;       // 16-byte vectors per chunk row: 8 (fp32) or 4 (bf16)
+    const int rows_per_it = 32 / vec_per_row;
+    const int lr = lane / vec_per_row, lv = lane % vec_per_row;
+    const bool ld_ok = (((long long)p.ldc * esz) % 16) == 0;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int rem = tile % tiles_mn;
       int mti, nti;
       tile_mn(p, rem, mti, nti);
-      const int m0 = mti * BM;
+      const int m0 = mti * TM;
       int n0 = nti * BN, n_end = p.N;                // global column of tile column cc is n0 + cc
       if (p.conv_mode == 2) {
         // wgrad: every 64-column box of the tile is one (filter tap, 64-channel chunk); this warp's columns [col0, col0+64)
@@ -423,21 +471,21 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           n0 = 0; n_end = 0;
         }
       }
-      // per-column bias: lane j prefetches the bias of column (chunk base + j) BEFORE waiting for the accumulator (the load
-      // hides behind the main loop) and the chunk loop broadcasts it with shuffles.  (32 dependent __ldg per chunk in the
-      // loop cost ~7 us per tile: the compiler serialised them through two registers.)
-      const int m = m0 + row;
-      const bool m_ok = m < p.M;
-      float bias_m = 0.f;
-      if (p.bias_mode == 2 && m_ok) bias_m = __ldg(p.bias + m);
+      // bias prefetch BEFORE waiting for the accumulator (hidden behind the main loop): per-column bias — lane j holds the
+      // bias of column (chunk base + j), broadcast later with shuffles; per-row bias — one value per sub-tile row.
+      float bias_m0 = 0.f, bias_m1 = 0.f;
+      if (p.bias_mode == 2) {
+        if (m0 + row < p.M) bias_m0 = __ldg(p.bias + m0 + row);
+        if (MT == 2 && m0 + BM + row < p.M) bias_m1 = __ldg(p.bias + m0 + BM + row);
+      }
       float bias_c0 = 0.f, bias_c1 = 0.f;
       if (p.bias_mode == 1 && active) {
         const int cb = n0 + col0 + lane;
         if (cb < n_end) bias_c0 = __ldg(p.bias + cb);
-        if (COLS_PER_WARP > 32 && cb + 32 < n_end) bias_c1 = __ldg(p.bias + cb + 32);
+        if (NCHUNK > 1 && cb + 32 < n_end) bias_c1 = __ldg(p.bias + cb + 32);
       }
       const int acc = t & 1;
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * C::ACC_COLS);
       mbar_wait(tmem_full_bar(acc), (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       if (!active) {                               // nothing to read: just hand the accumulator back
@@ -445,95 +493,97 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
         continue;
       }
-      // Fast path: whole tile in range and 16-byte aligned → staged, fully coalesced 16 B row stores
-      // (plain stores, or vector reductions red.global.add.v4.f32 for split-K).
-      const bool staged = (n0 + col0 + COLS_PER_WARP <= n_end) && (((long long)p.ldc * esz) % 16 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(p.C) + (long long)(n0 + col0) * esz) % 16 == 0);
 #pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
-        uint32_t r[32];
-        const int cc = col0 + 32 * c;                // column offset inside the tile
-        __syncwarp();                                // tcgen05.ld is .sync.aligned: reconverge first
-        tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, r);
-        tmem_ld_wait();
-        if (c == COLS_PER_WARP / 32 - 1) {
-          // all of this warp's TMEM reads for the tile are done → hand the accumulator back to the MMA thread
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-        }
-        const int nb = n0 + cc;
-        const float bias_sel = (c == 0) ? bias_c0 : bias_c1;
-        float v[32];
-        if (p.bias_mode == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, __shfl_sync(0xffffffffu, bias_sel, j));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias_m);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (!staged && (!m_ok || nb >= n_end)) continue;
-        if (staged) {
-          uint8_t* dst = stage_ptr + (size_t)row * pitch + (size_t)cc * esz;
-          if (p.out_bf16) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int u = 0; u < MT; ++u) {
+        const int mbase = m0 + u * BM;               // first row of this sub-tile
+        const int m = mbase + row;
+        const bool m_ok = m < p.M;
+#pragma unroll 1
+        for (int c = 0; c < NCHUNK; ++c) {
+          uint32_t r[32];
+          const int cc = col0 + 32 * c;              // column offset inside the tile
+          __syncwarp();                              // tcgen05.ld is .sync.aligned: reconverge first
+          tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)(u * BN + cc), r);
+          tmem_ld_wait();
+          if (u == MT - 1 && c == NCHUNK - 1) {
+            // all of this warp's TMEM reads for the tile are done → hand the accumulator back to the MMA thread
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
           }
-          continue;
-        }
-        const bool full = (nb + 32 <= n_end);
-        if (p.atomic_out) {
-          float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+          if (mbase >= p.M) continue;                // warp-uniform: whole sub-tile out of range
+          const int nb = n0 + cc;
+          const float bias_sel = (c == 0) ? bias_c0 : bias_c1;
+          float v[32];
+          if (p.bias_mode == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
-        } else if (p.out_bf16) {
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, __shfl_sync(0xffffffffu, bias_sel, j));
           } else {
+            const float bm = (u == 0) ? bias_m0 : bias_m1;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = f_to_bf16(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bm);
           }
-        } else {
-          float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
-          if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+          if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = v[j];
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
-        }
-      }
-      if (staged) {
-        // each warp re-reads only the (32 rows x its column half) it staged itself → a warp-level sync is enough
-        __syncwarp();
-        const int vec_per_row = (COLS_PER_WARP * esz) / 16;      // 16-byte vectors per row of this warp's region (<= 32)
-        const int rows_per_it = 32 / vec_per_row;
-        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)(n0 + col0) * esz;
-        const int lr = lane / vec_per_row, lv = lane % vec_per_row;
-        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
-          const int rr = 32 * q + r0 + lr;
-          if (m0 + rr < p.M) {
-            const uint4 val = *reinterpret_cast<const uint4*>(stage_ptr + (size_t)rr * pitch + (size_t)col0 * esz + (size_t)lv * 16);
-            uint8_t* gp = gbase + (long long)(m0 + rr) * p.ldc * esz + (long long)lv * 16;
-            if (p.atomic_out) {
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(val.x)),
-                           "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
+          // Fast path: chunk fully in range and 16-byte aligned → transposed through smem, coalesced 16 B row-segment
+          // stores (plain, or vector reductions red.global.add.v4.f32 for split-K).
+          const bool staged = (nb + 32 <= n_end) && ld_ok && (((reinterpret_cast<uintptr_t>(p.C) + (long long)nb * esz) % 16) == 0);
+          if (staged) {
+            uint8_t* dst = wstage + (size_t)lane * pitch;
+            if (p.out_bf16) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j * 2) = pk; }
             } else {
-              *reinterpret_cast<uint4*>(gp) = val;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            __syncwarp();
+            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)nb * esz + (long long)lv * 16;
+            for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
+              const int rr = r0 + lr;                                  // row inside this warp's 32-row band
+              const long long gm = (long long)mbase + 32 * q + rr;
+              if (gm < p.M) {
+                const uint4 val = *reinterpret_cast<const uint4*>(wstage + (size_t)rr * pitch + (size_t)lv * 16);
+                uint8_t* gp = gbase + gm * p.ldc * esz;
+                if (p.atomic_out) {
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(val.x)),
+                               "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
+                } else {
+                  *reinterpret_cast<uint4*>(gp) = val;
+                }
+              }
+            }
+            __syncwarp();                                              // staging region is free for the next chunk
+            continue;
+          }
+          if (!m_ok || nb >= n_end) continue;
+          const bool full = (nb + 32 <= n_end);
+          if (p.atomic_out) {
+            float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
+          } else if (p.out_bf16) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = f_to_bf16(v[j]);
+            }
+          } else {
+            float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+            if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = v[j];
             }
           }
         }
-        __syncwarp();                                            // staging region is free for the next tile
       }
     }
   }
@@ -586,6 +636,8 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
   return m;
 }
 
+static int g_dbg = 0;
+
 // Split-K factor for a persistent grid of `sms` CTAs walking equal-length tiles round-robin: minimise
 // waves x (k-blocks per slice + per-tile overhead).  A plain ceil(sms / tiles) overshoots the machine by a few tiles
 // and pays a whole second wave for them (conv2 wgrad: 13 tiles x 12 slices = 156 > 148).
@@ -605,22 +657,29 @@ static int choose_splits(int tiles, int num_kb, int sms) {
   return best;
 }
 
-static int g_dbg = 0;
-
-template <int BN>
+template <int BN, int MT>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, MT>;
   p.dbg = g_dbg;
   static bool attr_set = false;
   if (!attr_set) {
-    check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
+    check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
     attr_set = true;
   }
+  if (MT == 2 && !p.out_bf16) throw std::runtime_error("tmpi_native: 256-row GEMM tiles are bf16-output only");
   const long long total = (long long)p.mt * p.nt * splits;
   const int grid = (int)std::min<long long>(total, (long long)sm_count());
-  gemm_bf16_tcgen05<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_bf16_tcgen05<BN, MT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   count_launch();
   TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
+}
+
+// 256-row tiles (MT = 2) when the output is bf16 (no split-K) and there are still enough tiles to fill the machine
+static bool use_tall_tiles(long long M, int nt, int out_bf16, int sms) {
+  static const bool enabled = [] { const char* e = getenv("TMPI_GEMM_TALL"); return !(e && e[0] == '0'); }();
+  if (!enabled || !out_bf16 || M < 2 * BM) return false;
+  const long long tiles = ((M + 2 * BM - 1) / (2 * BM)) * nt;
+  return tiles * 2 >= sms;
 }
 
 }  // namespace gemm
@@ -663,8 +722,9 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   Params p;
   p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
-  p.mt = mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
-  p.group_m = (mt > 16 && nt > 16) ? 12 : 0;
+  const bool tall = splits == 1 && BN >= 64 && use_tall_tiles(M, nt, out_bf16, sms);
+  p.mt = tall ? (M + 2 * BM - 1) / (2 * BM) : mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
+  p.group_m = (p.mt > 12 && nt > 12) ? (tall ? 8 : 12) : 0;
   p.cHo = p.cWo = p.cS = p.cP = p.cKH = p.cKW = p.cCg = p.c_chunks = 0;
   if (splits > 1) {
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
@@ -674,9 +734,10 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
                         : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, (uint32_t)BM);
   CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64u)
                         : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN);
-  if (BN == 128) launch<128>(ta, tb, p, splits, st);
-  else if (BN == 64) launch<64>(ta, tb, p, splits, st);
-  else launch<32>(ta, tb, p, splits, st);
+  if (tall) { if (BN == 128) launch<128, 2>(ta, tb, p, splits, st); else launch<64, 2>(ta, tb, p, splits, st); }
+  else if (BN == 128) launch<128, 1>(ta, tb, p, splits, st);
+  else if (BN == 64) launch<64, 1>(ta, tb, p, splits, st);
+  else launch<32, 1>(ta, tb, p, splits, st);
 }
 
 // ------------------------------------------------------------------ implicit-GEMM convolution (TMA im2col)
@@ -726,19 +787,19 @@ static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot,
 }
 
 // weights [O][KH*KW][Cg] (bf16, contiguous) as a 3-D tiled map, box {64 ch, 1 tap, box_o out-channels}
-static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o) {
+static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o, int box_c = 64) {
   if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (Cg % 8) != 0) throw std::runtime_error("tmpi_native: conv weights must be 16B aligned, C % 8 == 0");
-  using Key = std::tuple<const void*, int, int, int, int>;
+  using Key = std::tuple<const void*, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{w, O, taps, Cg, box_o};
+  Key key{w, O, taps, Cg, box_o, box_c};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint64_t dims[3] = {(cuuint64_t)Cg, (cuuint64_t)taps, (cuuint64_t)O};
   cuuint64_t strides[2] = {(cuuint64_t)Cg * 2, (cuuint64_t)taps * Cg * 2};
-  cuuint32_t box[3] = {64u, 1u, (cuuint32_t)box_o};
+  cuuint32_t box[3] = {(cuuint32_t)box_c, 1u, (cuuint32_t)box_o};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -751,23 +812,30 @@ static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int b
 }  // namespace gemm
 
 // y[N*Ho*Wo, O] (ld = ldc, bf16) = relu(conv(x[.., c_off:c_off+Cg], w[O][KH][KW][Cg]) + bias)   — no col matrix in memory
+// dgrad = 1: the same kernel computes the input gradient — x is dy, (Cg, O) are (#dy channels, #dx channels) and w is the
+// FORWARD filter [Cg][KH][KW][O], read mirrored and transposed by the TMA loads (stride-1 convolutions only).
 void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
-                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, cudaStream_t st) {
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st) {
   using namespace gemm;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0 || O <= 0) return;
   if (M >= (1LL << 31)) throw std::runtime_error("conv_fprop: too many output pixels");
   const int BN = O > 64 ? 128 : 64;
   Params p;
-  p.C = y; p.bias = bias; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = 0;
+  p.C = y; p.bias = bias; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = dgrad ? 1 : 0;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? 1 : 0; p.relu = relu; p.atomic_out = 0;
-  p.mt = (int)((M + BM - 1) / BM); p.nt = (O + BN - 1) / BN; p.splits = 1;
+  if (dgrad && (S != 1 || (O % 8) != 0)) throw std::runtime_error("conv dgrad through the fprop kernel needs stride 1 and C % 8 == 0");
+  p.nt = (O + BN - 1) / BN; p.splits = 1;
+  const bool tall = use_tall_tiles(M, p.nt, out_bf16, sm_count());
+  p.mt = tall ? (int)((M + 2 * BM - 1) / (2 * BM)) : (int)((M + BM - 1) / BM);
   p.group_m = 0;
   p.conv_mode = 1; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BK - 1) / BK;
   p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
   CUtensorMap ta = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BM);
-  CUtensorMap tb = make_weight_map(w, O, KH * KW, Cg, BN);
-  if (BN == 128) launch<128>(ta, tb, p, 1, st); else launch<64>(ta, tb, p, 1, st);
+  CUtensorMap tb = dgrad ? make_weight_map(w, Cg, KH * KW, O, 64, 64) : make_weight_map(w, O, KH * KW, Cg, BN);
+  if (tall) { if (BN == 128) launch<128, 2>(ta, tb, p, 1, st); else launch<64, 2>(ta, tb, p, 1, st); }
+  else if (BN == 128) launch<128, 1>(ta, tb, p, 1, st);
+  else launch<64, 1>(ta, tb, p, 1, st);
 }
 
 // dw[O][KH*KW][Cg] (fp32, contiguous) = sum over pixels dy[pix, o] * im2col(x)[pix, (tap, c)]   (dy: [M, O] bf16, row pitch ldy)
@@ -793,7 +861,7 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
   if (splits > 1) check_cuda(cudaMemsetAsync(dw, 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
   CUtensorMap ta = make_tmap(dy, (uint64_t)O, (uint64_t)M, (uint64_t)ldy * 2, 64u);
   CUtensorMap tb = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BK);
-  if (BN == 128) launch<128>(ta, tb, p, splits, st); else launch<64>(ta, tb, p, splits, st);
+  if (BN == 128) launch<128, 1>(ta, tb, p, splits, st); else launch<64, 1>(ta, tb, p, splits, st);
 }
 
 }  // namespace tmpi

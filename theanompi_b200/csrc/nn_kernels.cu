@@ -17,10 +17,10 @@ template <int HALF>
 __global__ void lrn_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long rows, int C,
                                float k, float alpha, float beta) {
   const int nvec = C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * nvec) return;
-  const long long r = idx / nvec;
-  const int cv = (int)(idx % nvec);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;           // host guarantees rows * nvec < 2^32
+  if (idx >= (unsigned)rows * (unsigned)nvec) return;
+  const long long r = idx / (unsigned)nvec;
+  const int cv = (int)(idx - (unsigned)r * (unsigned)nvec);
   const __nv_bfloat16* row = x + r * C;
   float xs[24];
 #pragma unroll
@@ -48,10 +48,10 @@ template <int HALF>
 __global__ void lrn_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
                                __nv_bfloat16* __restrict__ dx, long long rows, int C, float k, float alpha, float beta) {
   const int nvec = C >> 3;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * nvec) return;
-  const long long r = idx / nvec;
-  const int cv = (int)(idx % nvec);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;           // host guarantees rows * nvec < 2^32
+  if (idx >= (unsigned)rows * (unsigned)nvec) return;
+  const long long r = idx / (unsigned)nvec;
+  const int cv = (int)(idx - (unsigned)r * (unsigned)nvec);
   float xs[24], ds[24];
 #pragma unroll
   for (int v = 0; v < 3; ++v) {
@@ -93,6 +93,7 @@ void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, floa
   if (C % 8) throw std::runtime_error("lrn: C must be a multiple of 8");
   const int half = n / 2;
   long long total = rows * (C / 8);
+  if (total >= (1LL << 32)) throw std::runtime_error("lrn: tensor too large for 32-bit indexing");
   const int B = 256;
   auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
   switch (half) {
@@ -109,6 +110,7 @@ void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int
   if (C % 8) throw std::runtime_error("lrn: C must be a multiple of 8");
   const int half = n / 2;
   long long total = rows * (C / 8);
+  if (total >= (1LL << 32)) throw std::runtime_error("lrn: tensor too large for 32-bit indexing");
   const int B = 256;
   auto X = (const __nv_bfloat16*)x; auto DY = (const __nv_bfloat16*)dy; auto DX = (__nv_bfloat16*)dx;
   switch (half) {
@@ -124,36 +126,64 @@ void lrn_bwd(const void* x, const void* dy, void* dx, long long rows, int C, int
 // ============================================================================ pooling
 struct PoolGeom { int N, H, W, C, Ho, Wo, k, s, p; };
 
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
-                                   uint8_t* __restrict__ arg, PoolGeom g) {
+template <int MAXW, bool FUSE>      // defined with the fused conv→pool backward further down
+__global__ void maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+                                             const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dym,
+                                             float* __restrict__ db0, float* __restrict__ db1, int c_split, PoolGeom g, int VT);
+
+// One CTA per output row (n, ho): (n, ho) come from blockIdx, threads sweep (wo, channel vector) — no per-thread
+// division chain, 32-bit offsets inside the row (the one-thread-per-output version was instruction bound at 2.5x the
+// memory roofline).  K > 0: compile-time window size (unrolled), K == 0: generic.
+template <int K>
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                          uint8_t* __restrict__ arg, PoolGeom g) {
   const int nvec = g.C >> 3;
-  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;             // host guarantees total < 2^32
-  const unsigned total = (unsigned)g.N * g.Ho * g.Wo * nvec;
-  if (idx >= total) return;
-  const int cv = (int)(idx % (unsigned)nvec); unsigned t = idx / (unsigned)nvec;
-  const int wo = (int)(t % g.Wo); t /= g.Wo;
-  const int ho = (int)(t % g.Ho); const int n = (int)(t / g.Ho);
-  float best[8]; int bi[8];
+  const int ho = blockIdx.x % g.Ho, n = blockIdx.x / g.Ho;
+  const int h0 = ho * g.s - g.p;
+  const __nv_bfloat16* xin = x + (long long)n * g.H * g.W * g.C;
+  const long long orow = ((long long)n * g.Ho + ho) * g.Wo * g.C;
+  const int items = g.Wo * nvec;
+  for (int it = threadIdx.x; it < items; it += blockDim.x) {
+    const int wo = it / nvec, cv = it - wo * nvec;
+    const int w0 = wo * g.s - g.p;
+    float best[8]; int bi[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
-  for (int kh = 0; kh < g.k; ++kh) {
-    const int h = ho * g.s - g.p + kh;
-    if (h < 0 || h >= g.H) continue;
-    for (int kw = 0; kw < g.k; ++kw) {
-      const int w = wo * g.s - g.p + kw;
-      if (w < 0 || w >= g.W) continue;
-      float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(x + (((long long)n * g.H + h) * g.W + w) * g.C + cv * 8), v);
+    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+    if (K > 0) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * g.k + kw; }
+      for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+        for (int kw = 0; kw < K; ++kw) {
+          const int h = h0 + kh, w = w0 + kw;
+          if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
+            float v[8];
+            unpack8(*reinterpret_cast<const bf16x8*>(xin + ((unsigned)(h * g.W + w) * (unsigned)g.C + cv * 8)), v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * K + kw; }
+          }
+        }
+      }
+    } else {
+      for (int kh = 0; kh < g.k; ++kh) {
+        const int h = h0 + kh;
+        if (h < 0 || h >= g.H) continue;
+        for (int kw = 0; kw < g.k; ++kw) {
+          const int w = w0 + kw;
+          if (w < 0 || w >= g.W) continue;
+          float v[8];
+          unpack8(*reinterpret_cast<const bf16x8*>(xin + ((unsigned)(h * g.W + w) * (unsigned)g.C + cv * 8)), v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * g.k + kw; }
+        }
+      }
     }
+    const long long o = orow + (unsigned)(wo * g.C + cv * 8);
+    *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
+    uint2 packed;
+    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint2*>(arg + o) = packed;
   }
-  const long long o = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8;
-  *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
-  uint2 packed;
-  packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-  packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-  *reinterpret_cast<uint2*>(arg + o) = packed;
 }
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ arg,
@@ -263,15 +293,31 @@ void pool_fwd(const void* x, void* y, void* arg, int N, int H, int W, int C, int
   PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
   long long total = (long long)N * Ho * Wo * (C / 8);
   if ((long long)N * H * W * (C / 8) >= (1LL << 32)) throw std::runtime_error("pool: tensor too large for 32-bit indexing");
-  if (is_max) maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (uint8_t*)arg, g);
-  else avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
+  if ((long long)H * W * C >= (1LL << 31)) throw std::runtime_error("pool: image too large for 32-bit in-image offsets");
+  if (is_max) {
+    const unsigned rows = (unsigned)N * Ho;
+    auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y; auto A = (uint8_t*)arg;
+    if (k == 3) maxpool_fwd_kernel<3><<<rows, 256, 0, st>>>(X, Y, A, g);
+    else if (k == 2) maxpool_fwd_kernel<2><<<rows, 256, 0, st>>>(X, Y, A, g);
+    else maxpool_fwd_kernel<0><<<rows, 256, 0, st>>>(X, Y, A, g);
+  } else avgpool_fwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, g);
   count_launch(); TMPI_CHECK_LAUNCH("pool_fwd"); ::tmpi::check_capture(st, "pool_fwd");
 }
 
 void pool_bwd(const void* dy, const void* arg, void* dx, int N, int H, int W, int C, int Ho, int Wo, int k, int s, int p, int is_max, cudaStream_t st) {
   PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
   long long total = (long long)N * H * W * (C / 8);
-  if (is_max) maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)arg, (__nv_bfloat16*)dx, g);
+  const int maxw = (k + s - 1) / s;
+  if (is_max && maxw <= 3 && (long long)H * W * C < (1LL << 31)) {
+    // row-per-CTA kernel shared with the fused conv→pool backward (all candidate windows in flight at once)
+    const int nvec = C / 8;
+    const int VT = nvec < 32 ? nvec : 32;
+    dim3 grid((unsigned)N * H, (unsigned)((nvec + VT - 1) / VT));
+    auto DY = (const __nv_bfloat16*)dy; auto A = (const uint8_t*)arg; auto DX = (__nv_bfloat16*)dx;
+    if (maxw == 1) maxpool_relu_bias_bwd_kernel<1, false><<<grid, 256, 0, st>>>(DY, A, nullptr, DX, nullptr, nullptr, C, g, VT);
+    else if (maxw == 2) maxpool_relu_bias_bwd_kernel<2, false><<<grid, 256, 0, st>>>(DY, A, nullptr, DX, nullptr, nullptr, C, g, VT);
+    else maxpool_relu_bias_bwd_kernel<3, false><<<grid, 256, 0, st>>>(DY, A, nullptr, DX, nullptr, nullptr, C, g, VT);
+  } else if (is_max) maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (const uint8_t*)arg, (__nv_bfloat16*)dx, g);
   else avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, g);
   count_launch(); TMPI_CHECK_LAUNCH("pool_bwd"); ::tmpi::check_capture(st, "pool_bwd");
 }
@@ -433,18 +479,35 @@ __global__ void relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   if (tr < RL && cv < nvec) {
-    for (long long r = r0 + tr; r < min(R, r0 + rows_per_cta); r += RL) {
-      float d[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(dy + r * ld + cv * 8), d);
-      if (RELU) {
-        float v[8];
-        unpack8(*reinterpret_cast<const bf16x8*>(y + r * ld + cv * 8), v);
+    const long long rend = min(R, r0 + rows_per_cta);
+    for (long long r = r0 + tr; r < rend; r += 4 * RL) {
+      // 4 rows per trip, all loads issued before any use (memory-level parallelism: this kernel is pure streaming)
+      bf16x8 dv[4], yv[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) d[i] = 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * RL;
+        if (rr < rend) {
+          dv[u] = *reinterpret_cast<const bf16x8*>(dy + rr * ld + cv * 8);
+          if (RELU) yv[u] = *reinterpret_cast<const bf16x8*>(y + rr * ld + cv * 8);
+        }
       }
-      if (WRITE) *reinterpret_cast<bf16x8*>(dym + r * C + cv * 8) = pack8(d);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += d[i];
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * RL;
+        if (rr < rend) {
+          float d[8];
+          unpack8(dv[u], d);
+          if (RELU) {
+            float v[8];
+            unpack8(yv[u], v);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) d[i] = 0.f;
+          }
+          if (WRITE) *reinterpret_cast<bf16x8*>(dym + rr * C + cv * 8) = pack8(d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += d[i];
+        }
+      }
     }
   }
   if (db == nullptr) return;
@@ -469,7 +532,7 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
   const int nvec = C / 8;
   const int VT = nvec < 32 ? nvec : 32;
   const int RL = 256 / VT;
-  const int rows_per_cta = RL * 16;
+  const int rows_per_cta = RL * 8;
   dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
   if (db) check_cuda(cudaMemsetAsync(db, 0, (size_t)C * 4, st), "relu_bias_bwd memset");
@@ -487,63 +550,86 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
 //   db[c]       += sum_{n,h,w} dym                                                                 (pre-zeroed by the launcher)
 // Channels < c_split accumulate into db0, the rest into db1 (the two parameter sets of a 2-group AlexNet block).
 // Replaces maxpool_bwd (write dx) + relu_bias_bwd (read dx, read y, write dym): 2 reads + 2 writes of the big tensor -> 1 + 1.
-__global__ void maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
+// One CTA per input row (n, h): the candidate output rows are CTA-uniform, each thread owns one channel vector (so its bias
+// partial sums stay in registers) and sweeps w.
+template <int MAXW, bool FUSE>
+__global__ void __launch_bounds__(256) maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ arg,
                                              const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dym,
-                                             float* __restrict__ db0, float* __restrict__ db1, int c_split, PoolGeom g,
-                                             int VT, int rows_per_cta) {
+                                             float* __restrict__ db0, float* __restrict__ db1, int c_split, PoolGeom g, int VT) {
   extern __shared__ float sm[];                       // [RL][VT*8]
   const int nvec = g.C >> 3;
   const int RL = blockDim.x / VT;
-  const int tv = threadIdx.x % VT, tr = threadIdx.x / VT;
+  const int tv = threadIdx.x % VT, tw = threadIdx.x / VT;
   const int cv = blockIdx.y * VT + tv;
-  const long long R = (long long)g.N * g.H * g.W;
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const int h = blockIdx.x % g.H, n = blockIdx.x / g.H;
+  int ho_lo = (h + g.p - g.k + g.s) / g.s; if (h + g.p - g.k + 1 <= 0) ho_lo = 0;
+  const int ho_hi = min(g.Ho - 1, (h + g.p) / g.s);
+  const long long irow = ((long long)n * g.H + h) * g.W * g.C;
+  const long long obase = (long long)n * g.Ho * g.Wo * g.C;
   float tot[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot[i] = 0.f;
-  if (tr < RL && cv < nvec) {
-    for (long long r = r0 + tr; r < min(R, r0 + rows_per_cta); r += RL) {
-      const int w = (int)(r % g.W); const long long t = r / g.W;
-      const int h = (int)(t % g.H); const int n = (int)(t / g.H);
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      int ho_lo = (h + g.p - g.k + g.s) / g.s; if (h + g.p - g.k + 1 <= 0) ho_lo = 0;
+  if (tw < RL && cv < nvec) {
+    for (int w = tw; w < g.W; w += RL) {
       int wo_lo = (w + g.p - g.k + g.s) / g.s; if (w + g.p - g.k + 1 <= 0) wo_lo = 0;
-      const int ho_hi = min(g.Ho - 1, (h + g.p) / g.s);
       const int wo_hi = min(g.Wo - 1, (w + g.p) / g.s);
-      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
-        const int kh = h + g.p - ho * g.s;
-        if (kh < 0 || kh >= g.k) continue;
-        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-          const int kw = w + g.p - wo * g.s;
-          if (kw < 0 || kw >= g.k) continue;
-          const long long o = (((long long)n * g.Ho + ho) * g.Wo + wo) * g.C + cv * 8;
-          const uint2 a = *reinterpret_cast<const uint2*>(arg + o);
-          float d[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(dyp + o), d);
-          const uint32_t me = (uint32_t)(kh * g.k + kw);
+      // phase 1: all candidate windows (at most MAXW x MAXW = ceil(k/s)^2) and the activation in flight at once
+      uint2 av[MAXW * MAXW];
+      bf16x8 dv[MAXW * MAXW];
+      uint32_t me[MAXW * MAXW];
+      bool ok[MAXW * MAXW];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t ai = ((i < 4 ? a.x : a.y) >> (8 * (i & 3))) & 0xFFu;
-            if (ai == me) acc[i] += d[i];
+      for (int a = 0; a < MAXW; ++a) {
+#pragma unroll
+        for (int b = 0; b < MAXW; ++b) {
+          const int ho = ho_lo + a, wo = wo_lo + b;
+          const int t = a * MAXW + b;
+          ok[t] = (ho <= ho_hi && wo <= wo_hi);
+          me[t] = (uint32_t)((h + g.p - ho * g.s) * g.k + (w + g.p - wo * g.s));
+          if (ok[t]) {
+            const long long o = obase + (unsigned)((ho * g.Wo + wo) * g.C + cv * 8);
+            av[t] = *reinterpret_cast<const uint2*>(arg + o);
+            dv[t] = *reinterpret_cast<const bf16x8*>(dyp + o);
           }
         }
       }
-      float v[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(y + r * g.C + cv * 8), v);
+      const long long xi = irow + (unsigned)(w * g.C + cv * 8);
+      bf16x8 yv;
+      if (FUSE) yv = *reinterpret_cast<const bf16x8*>(y + xi);
+      float acc[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) acc[i] = 0.f;
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+      for (int t = 0; t < MAXW * MAXW; ++t) {
+        if (ok[t]) {
+          float d[8];
+          unpack8(dv[t], d);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t ai = ((i < 4 ? av[t].x : av[t].y) >> (8 * (i & 3))) & 0xFFu;
+            if (ai == me[t]) acc[i] += d[i];
+          }
+        }
+      }
+      if (FUSE) {
+        float v[8];
+        unpack8(yv, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) acc[i] = 0.f;
+      }
       const bf16x8 pk = pack8(acc);
-      *reinterpret_cast<bf16x8*>(dym + r * g.C + cv * 8) = pk;
-      unpack8(pk, acc);                                 // db sums what wgrad / dgrad will actually see (bf16-rounded)
+      *reinterpret_cast<bf16x8*>(dym + xi) = pk;
+      if (FUSE) {
+        unpack8(pk, acc);                               // db sums what wgrad / dgrad will actually see (bf16-rounded)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) tot[i] += acc[i];
+        for (int i = 0; i < 8; ++i) tot[i] += acc[i];
+      }
     }
   }
-  if (tr < RL) {
+  if (!FUSE) return;                                    // plain max-pool backward: no mask, no bias gradient
+  if (tw < RL) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sm[(tr * VT + tv) * 8 + i] = tot[i];
+    for (int i = 0; i < 8; ++i) sm[(tw * VT + tv) * 8 + i] = tot[i];
   }
   __syncthreads();
   if (threadIdx.x < VT * 8) {
@@ -560,19 +646,22 @@ __global__ void maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ d
 void maxpool_relu_bias_bwd(const void* dyp, const void* arg, const void* y, void* dym, void* db0, void* db1, int c_split, int N, int H,
                            int W, int C, int Ho, int Wo, int k, int s, int p, cudaStream_t st) {
   if (C % 8) throw std::runtime_error("maxpool_relu_bias_bwd: C must be a multiple of 8");
+  if ((long long)H * W * C >= (1LL << 31)) throw std::runtime_error("maxpool_relu_bias_bwd: image too large for 32-bit in-image offsets");
   PoolGeom g{N, H, W, C, Ho, Wo, k, s, p};
   const int nvec = C / 8;
   const int VT = nvec < 32 ? nvec : 32;
   const int RL = 256 / VT;
-  const int rows_per_cta = RL * 8;
-  const long long R = (long long)N * H * W;
-  dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
+  dim3 grid((unsigned)N * H, (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
   if (c_split > C) c_split = C;
   check_cuda(cudaMemsetAsync(db0, 0, (size_t)c_split * 4, st), "maxpool_relu_bias_bwd memset");
   if (c_split < C) check_cuda(cudaMemsetAsync(db1, 0, (size_t)(C - c_split) * 4, st), "maxpool_relu_bias_bwd memset");
-  maxpool_relu_bias_bwd_kernel<<<grid, 256, smem, st>>>((const __nv_bfloat16*)dyp, (const uint8_t*)arg, (const __nv_bfloat16*)y,
-                                                         (__nv_bfloat16*)dym, (float*)db0, (float*)db1, c_split, g, VT, rows_per_cta);
+  const int maxw = (k + s - 1) / s;
+  auto DYP = (const __nv_bfloat16*)dyp; auto A = (const uint8_t*)arg; auto Y = (const __nv_bfloat16*)y; auto DM = (__nv_bfloat16*)dym;
+  if (maxw == 1) maxpool_relu_bias_bwd_kernel<1, true><<<grid, 256, smem, st>>>(DYP, A, Y, DM, (float*)db0, (float*)db1, c_split, g, VT);
+  else if (maxw == 2) maxpool_relu_bias_bwd_kernel<2, true><<<grid, 256, smem, st>>>(DYP, A, Y, DM, (float*)db0, (float*)db1, c_split, g, VT);
+  else if (maxw == 3) maxpool_relu_bias_bwd_kernel<3, true><<<grid, 256, smem, st>>>(DYP, A, Y, DM, (float*)db0, (float*)db1, c_split, g, VT);
+  else throw std::runtime_error("maxpool_relu_bias_bwd: pooling windows overlapping more than 3x3 outputs are not supported");
   count_launch(); TMPI_CHECK_LAUNCH("maxpool_relu_bias_bwd"); ::tmpi::check_capture(st, "maxpool_relu_bias_bwd");
 }
 
@@ -782,27 +871,30 @@ void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cu
 // space-to-depth image x'[n, i, j, (dy*S+dx)*C + c] = x[n, S*i+dy, S*j+dx, c] with the re-indexed (zero padded) filter.
 // That turns AlexNet's conv1 (11x11/4 on RGB, which TMA cannot gather: 6-byte pixels) into a 3x3 conv on 48 channels
 // that runs on the implicit-GEMM tcgen05 path.
-__global__ void space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H, int W, int C, int S,
-                                      int Hs, int Ws, int Cp) {
-  const long long total = (long long)N * Hs * Ws * S;                 // one thread per (output pixel, dy): S*C contiguous inputs
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int dy = (int)(idx % S); long long t = idx / S;
-    const int j = (int)(t % Ws); t /= Ws;
-    const int i = (int)(t % Hs); const int n = (int)(t / Hs);
-    const int h = i * S + dy;
-    __nv_bfloat16* dst = y + (((long long)n * Hs + i) * Ws + j) * Cp + dy * S * C;
-    const __nv_bfloat16* src = x + (((long long)n * H + h) * W + (long long)j * S) * C;
-    for (int e = 0; e < S * C; ++e) {
-      const int w = j * S + e / C;
-      dst[e] = (h < H && w < W) ? src[e] : f_to_bf16(0.f);
+// One CTA per output row (n, i): for a fixed dy the S*C output channels of pixel j are S*C CONTIGUOUS input elements of image
+// row S*i+dy starting at j*S*C — a strided copy of short runs; threads sweep the row's output elements (coalesced stores).
+__global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
+                                                             int W, int C, int S, int Hs, int Ws, int Cp) {
+  const int i = blockIdx.x % Hs, n = blockIdx.x / Hs;
+  const int SC = S * C;                       // elements per (pixel, dy)
+  const int WC = W * C;
+  __nv_bfloat16* orow = y + ((long long)n * Hs + i) * Ws * Cp;
+  const __nv_bfloat16* irow0 = x + ((long long)n * H + (long long)i * S) * WC;
+  const int total = Ws * Cp;
+  const __nv_bfloat16 zero = f_to_bf16(0.f);
+  for (int o = threadIdx.x; o < total; o += blockDim.x) {
+    const int j = o / Cp, cp = o - j * Cp;
+    __nv_bfloat16 v = zero;
+    if (cp < S * SC) {
+      const int dy = cp / SC, e = cp - dy * SC;
+      const int col = j * SC + e;             // element inside input row S*i+dy
+      if (i * S + dy < H && col < WC) v = irow0[(unsigned)(dy * WC + col)];
     }
-    if (dy == 0) for (int e = S * S * C; e < Cp; ++e) dst[e] = f_to_bf16(0.f);      // channel padding (Cp multiple of 8)
+    orow[o] = v;
   }
 }
 void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st) {
-  const long long total = (long long)N * Hs * Ws * S;
-  space_to_depth_kernel<<<(int)std::min<long long>((total + 255) / 256, (long long)sm_count() * 32), 256, 0, st>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, S, Hs, Ws, Cp);
+  space_to_depth_kernel<<<(unsigned)N * Hs, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, S, Hs, Ws, Cp);
   count_launch(); TMPI_CHECK_LAUNCH("space_to_depth"); ::tmpi::check_capture(st, "space_to_depth");
 }
 
@@ -843,6 +935,8 @@ void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S,
 }
 
 // ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32
+// One CTA per output row (n, oy): crop offsets / flip flag are CTA-uniform, threads sweep the row's (ox, c) elements with 32-bit
+// math (coalesced stores; loads are contiguous runs of the source row, reversed when mirrored).
 template <typename Tin, typename Tout>
 __global__ void crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode, float scale,
                                         Tout* __restrict__ out, const int* __restrict__ offs, const uint8_t* __restrict__ flips,

@@ -212,7 +212,7 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
         # implicit GEMM: the activation tile is gathered by TMA im2col loads inside the kernel — no col matrix
         yp = y.data_ptr() + o_off * 2
         L().conv_fprop(x.data_ptr(), wb.data_ptr(), yp, _p(b), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
-                       Og, Ot, int(bool(relu)), 1, _st(x))
+                       Og, Ot, int(bool(relu)), 1, 0, _st(x))
         return None
     col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
     w2 = _w2d(w, K, Kp)
@@ -248,7 +248,7 @@ def _conv_s2d_fwd(x, w, b, relu, g):
     L().s2d_filter(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 0, _st(x))
     y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=dev)
     L().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), _p(b), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O,
-                   int(bool(relu)), 1, _st(x))
+                   int(bool(relu)), 1, 0, _st(x))
     return y, xs
 
 
@@ -323,10 +323,10 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
                        Og, int(ldy), _st(x))
         if need_dx:
             if s == 1:
-                wt = torch.empty((Cg, KH, KW, Og), dtype=BF16, device=dev)
-                L().conv_weight_flip(wb.data_ptr(), wt.data_ptr(), Og, KH, KW, int(Cg), _st(x))
-                L().conv_fprop(dym.data_ptr() - dy_coff * 2, wt.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, int(ldy), int(dy_coff),
-                               Og, KH, KW, H, W, 1, KH - 1 - int(p), int(Cg), Ct, 0, 1, _st(x))
+                # dgrad = forward conv of dy with the mirrored, transposed filter — which the kernel's TMA loads read straight
+                # out of the forward weights (MN-major boxes of the mirrored tap): no flipped copy
+                L().conv_fprop(dym.data_ptr() - dy_coff * 2, wb.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, int(ldy), int(dy_coff),
+                               Og, KH, KW, H, W, 1, KH - 1 - int(p), int(Cg), Ct, 0, 1, 1, _st(x))
             else:
                 colK = KH * KW * Cg
                 Kp = (colK + 7) // 8 * 8

@@ -10,7 +10,7 @@ pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _torchrun(n, script, *args, port=29611, timeout=600):
+def _torchrun(n, script, *args, port=29611, timeout=300):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, script)] + list(args)
     return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, cwd=ROOT)
@@ -28,7 +28,7 @@ def test_bench_two_ranks_fused_matches_loss_scale():
     assert r.returncode == 0 and '"n_gpus": 2' in r.stdout, r.stdout[-4000:]
 
 
-def _run_rule(rule_cls, devices, cfg=None, env=None, timeout=600):
+def _run_rule(rule_cls, devices, cfg=None, env=None, timeout=240):
     import subprocess
     rule = rule_cls()
     rule.model_config = dict(batch_size=64, file_batch_size=64, n_epochs=1, learning_rate=0.001, max_batches=12, printFreq=4,

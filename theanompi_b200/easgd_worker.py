@@ -29,7 +29,8 @@ class EASGD_Worker(MPI_GPU_Process):
         self.server_rank = 0
         self.worker_id = os.getpid()
         self.verbose = False
-        self.register_worker()
+        # registration happens in main() AFTER the model is built: building allocates the symmetric peer arena, a
+        # collective over server + workers — a worker blocked on the server's reply here would deadlock it on GPU
 
     def arena_allocator(self):
         if self.kind != "cuda" or self.size < 2:
@@ -168,6 +169,11 @@ def main(argv=None):
         config.update(json.loads(os.environ["TMPI_MODEL_CONFIG"]))
     from .worker import load_model_class
     model = load_model_class(modelfile, modelclass)(config)
+    worker.register_worker()                                  # first registrant becomes the recording / validating worker
+    if worker.verbose:
+        config["verbose"] = True
+        if hasattr(model, "verbose"):
+            model.verbose = True
     worker.build(model, config)
     worker.run(model, exchange_freq=config.get("exchange_freq"))
     worker.finalize()

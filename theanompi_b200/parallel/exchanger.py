@@ -21,6 +21,8 @@ B200-native hot paths (no NCCL / MPI call on them):
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -143,7 +145,8 @@ class BSP_Exchanger(object):
         mu = m.mu if m.use_momentum else 0.0
         blocks = self.comm_blocks
         if blocks is None and self.overlap:
-            blocks = 32 if (b["hi"] - b["lo"]) * 4 > (8 << 20) else 8
+            big = int(os.environ.get("TMPI_OVERLAP_BLOCKS", "64"))     # measured at 2 ranks: 16 → 4.5 ms, 32 → 3.1, 64 → 2.17, 148 → 2.28
+            blocks = big if (b["hi"] - b["lo"]) * 4 > (8 << 20) else min(8, big)
         self.gpucomm.fused_allreduce_sgd(self.arena, b["lo"], b["hi"], mu, m.use_nesterov_momentum,
                                          algo=self.algo, wire16=self.wire16, max_blocks=blocks)
 

@@ -602,22 +602,27 @@ __global__ void __launch_bounds__(256) maxpool_relu_bias_bwd_kernel(const __nv_b
 #pragma unroll
       for (int t = 0; t < MAXW * MAXW; ++t) {
         if (ok[t]) {
-          float d[8];
-          unpack8(dv[t], d);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t ai = ((i < 4 ? av[t].x : av[t].y) >> (8 * (i & 3))) & 0xFFu;
-            if (ai == me[t]) acc[i] += d[i];
-          }
+          // argmax match for 4 channels per instruction (__vcmpeq4 on the packed argmax bytes), byte mask widened to the
+          // bf16 lanes with PRMT, gradient kept packed until the add
+          const uint32_t me4 = me[t] * 0x01010101u;
+          const uint32_t eq_lo = __vcmpeq4(av[t].x, me4), eq_hi = __vcmpeq4(av[t].y, me4);
+          const uint32_t* dw = reinterpret_cast<const uint32_t*>(&dv[t]);
+          const uint32_t w0 = dw[0] & __byte_perm(eq_lo, 0, 0x1100), w1 = dw[1] & __byte_perm(eq_lo, 0, 0x3322);
+          const uint32_t w2 = dw[2] & __byte_perm(eq_hi, 0, 0x1100), w3 = dw[3] & __byte_perm(eq_hi, 0, 0x3322);
+          acc[0] += __uint_as_float(w0 << 16); acc[1] += __uint_as_float(w0 & 0xFFFF0000u);
+          acc[2] += __uint_as_float(w1 << 16); acc[3] += __uint_as_float(w1 & 0xFFFF0000u);
+          acc[4] += __uint_as_float(w2 << 16); acc[5] += __uint_as_float(w2 & 0xFFFF0000u);
+          acc[6] += __uint_as_float(w3 << 16); acc[7] += __uint_as_float(w3 & 0xFFFF0000u);
         }
       }
+      bf16x8 pk = pack8(acc);
       if (FUSE) {
-        float v[8];
-        unpack8(yv, v);
+        // ReLU mask on the packed result: a bf16 is > 0 exactly when its bits, read as int16, are > 0
+        uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+        const uint32_t* yw = reinterpret_cast<const uint32_t*>(&yv);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (!(v[i] > 0.f)) acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) pw[i] &= __vcmpgts2(yw[i], 0u);
       }
-      const bf16x8 pk = pack8(acc);
       *reinterpret_cast<bf16x8*>(dym + xi) = pk;
       if (FUSE) {
         unpack8(pk, acc);                               // db sums what wgrad / dgrad will actually see (bf16-rounded)
@@ -873,28 +878,32 @@ void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cu
 // that runs on the implicit-GEMM tcgen05 path.
 // One CTA per output row (n, i): for a fixed dy the S*C output channels of pixel j are S*C CONTIGUOUS input elements of image
 // row S*i+dy starting at j*S*C — a strided copy of short runs; threads sweep the row's output elements (coalesced stores).
+template <int SCT>
 __global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
                                                              int W, int C, int S, int Hs, int Ws, int Cp) {
+  // blockDim = (Cp, 256 / Cp): threadIdx.x = output channel cp, threadIdx.y strides over the pixels j of output row (n, i).
+  // SCT > 0: S*C is a compile-time constant, so cp / SC and cp % SC are a multiply-shift (the generic version was
+  // issue-bound on runtime divisions: 74 instructions per 2-byte element).
   const int i = blockIdx.x % Hs, n = blockIdx.x / Hs;
-  const int SC = S * C;                       // elements per (pixel, dy)
+  const int SC = SCT > 0 ? SCT : S * C;
   const int WC = W * C;
-  __nv_bfloat16* orow = y + ((long long)n * Hs + i) * Ws * Cp;
-  const __nv_bfloat16* irow0 = x + ((long long)n * H + (long long)i * S) * WC;
-  const int total = Ws * Cp;
+  const int cp = threadIdx.x;
+  const int dy = cp / SC, e = cp - dy * SC;
+  const bool chan_ok = cp < S * SC && (i * S + dy) < H;
+  __nv_bfloat16* orow = y + ((long long)n * Hs + i) * Ws * Cp + cp;
+  const __nv_bfloat16* irow = x + ((long long)n * H + (long long)i * S) * WC + (unsigned)(dy * WC + e);
   const __nv_bfloat16 zero = f_to_bf16(0.f);
-  for (int o = threadIdx.x; o < total; o += blockDim.x) {
-    const int j = o / Cp, cp = o - j * Cp;
-    __nv_bfloat16 v = zero;
-    if (cp < S * SC) {
-      const int dy = cp / SC, e = cp - dy * SC;
-      const int col = j * SC + e;             // element inside input row S*i+dy
-      if (i * S + dy < H && col < WC) v = irow0[(unsigned)(dy * WC + col)];
-    }
-    orow[o] = v;
+  for (int j = threadIdx.y; j < Ws; j += blockDim.y) {
+    const int col = j * SC;
+    orow[(unsigned)(j * Cp)] = (chan_ok && col + e < WC) ? irow[col] : zero;
   }
 }
 void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st) {
-  space_to_depth_kernel<<<(unsigned)N * Hs, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, N, H, W, C, S, Hs, Ws, Cp);
+  if (Cp > 256) throw std::runtime_error("space_to_depth: more than 256 packed channels");
+  const dim3 blk((unsigned)Cp, (unsigned)std::max(1, 256 / Cp));
+  auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
+  if (S * C == 12) space_to_depth_kernel<12><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp);
+  else space_to_depth_kernel<0><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp);
   count_launch(); TMPI_CHECK_LAUNCH("space_to_depth"); ::tmpi::check_capture(st, "space_to_depth");
 }
 
@@ -937,26 +946,32 @@ void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S,
 // ============================================================================ loader: normalise + crop + mirror → NHWC bf16/fp32
 // One CTA per output row (n, oy): crop offsets / flip flag are CTA-uniform, threads sweep the row's (ox, c) elements with 32-bit
 // math (coalesced stores; loads are contiguous runs of the source row, reversed when mirrored).
+// grid = (N * ch, ceil(cw / 128)): the output row (n, oy) comes from blockIdx.x, the pixel from blockIdx.y / threadIdx.x — no
+// per-thread divisions (the one-thread-per-pixel version with 64-bit div/mod was issue-bound: 230 instructions per pixel).
 template <typename Tin, typename Tout>
-__global__ void crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode, float scale,
-                                        Tout* __restrict__ out, const int* __restrict__ offs, const uint8_t* __restrict__ flips,
+__global__ void __launch_bounds__(128) crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode,
+                                        float scale, Tout* __restrict__ out, const int* __restrict__ offs, const uint8_t* __restrict__ flips,
                                         int N, int H, int W, int C, int ch, int cw, int Cout) {
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)N * ch * cw;
-  if (idx >= total) return;
-  const int ox = (int)(idx % cw); long long t = idx / cw;
-  const int oy = (int)(t % ch); const int n = (int)(t / ch);
-  const int y0 = offs[2 * n], x0 = offs[2 * n + 1];
-  const int sy = y0 + oy;
-  const int sx = x0 + (flips[n] ? (cw - 1 - ox) : ox);
-  const long long sp = (((long long)n * H + sy) * W + sx) * C;
-  const long long mp = mean_mode == 2 ? ((long long)sy * W + sx) * C : 0;
-  Tout* o = out + idx * Cout;
+  const int ox = blockIdx.y * blockDim.x + threadIdx.x;
+  if (ox >= cw) return;
+  const int oy = blockIdx.x % ch, n = blockIdx.x / ch;
+  const int sy = offs[2 * n] + oy;
+  const int sx = offs[2 * n + 1] + (flips[n] ? (cw - 1 - ox) : ox);
+  const unsigned pix = (unsigned)(sy * W + sx) * (unsigned)C;          // inside one image (host checks H*W*C < 2^31)
+  const Tin* src = x + (long long)n * H * W * C + pix;
+  const float* mp = mean_mode == 2 ? mean + pix : mean;
+  Tout* o = out + ((long long)blockIdx.x * cw + ox) * Cout;
+  if (C == 3 && Cout == 3) {
+    const float m0 = mean_mode == 0 ? mp[0] : mp[0], m1 = mean_mode == 0 ? mp[0] : mp[1], m2 = mean_mode == 0 ? mp[0] : mp[2];
+    const float v0 = ((float)src[0] - m0) * scale, v1 = ((float)src[1] - m1) * scale, v2 = ((float)src[2] - m2) * scale;
+    o[0] = (Tout)v0; o[1] = (Tout)v1; o[2] = (Tout)v2;
+    return;
+  }
   for (int c = 0; c < Cout; ++c) {
     float v = 0.f;
     if (c < C) {
-      const float m = mean_mode == 0 ? mean[0] : (mean_mode == 1 ? mean[c] : mean[mp + c]);
-      v = ((float)x[sp + c] - m) * scale;
+      const float m = mean_mode == 0 ? mp[0] : mp[c];
+      v = ((float)src[c] - m) * scale;
     }
     o[c] = (Tout)v;
   }
@@ -964,10 +979,10 @@ __global__ void crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* 
 
 void crop_mirror_norm(const void* x, int in_kind /*0 u8, 1 bf16, 2 f32*/, const void* mean, int mean_mode, float scale, void* out,
                       int out_bf16, const void* offs, const void* flips, int N, int H, int W, int C, int ch, int cw, int Cout, cudaStream_t st) {
-  long long total = (long long)N * ch * cw;
-  const int g = grid_for(total, 256);
+  if ((long long)H * W * C >= (1LL << 31) || (long long)N * ch >= (1LL << 31)) throw std::runtime_error("crop_mirror_norm: image too large");
+  const dim3 g((unsigned)(N * ch), (unsigned)((cw + 127) / 128));
   auto M = (const float*)mean; auto O = (const int*)offs; auto F = (const uint8_t*)flips;
-#define CMN(TI, TO) crop_mirror_norm_kernel<TI, TO><<<g, 256, 0, st>>>((const TI*)x, M, mean_mode, scale, (TO*)out, O, F, N, H, W, C, ch, cw, Cout)
+#define CMN(TI, TO) crop_mirror_norm_kernel<TI, TO><<<g, 128, 0, st>>>((const TI*)x, M, mean_mode, scale, (TO*)out, O, F, N, H, W, C, ch, cw, Cout)
   if (in_kind == 0) { if (out_bf16) CMN(uint8_t, __nv_bfloat16); else CMN(uint8_t, float); }
   else if (in_kind == 1) { if (out_bf16) CMN(__nv_bfloat16, __nv_bfloat16); else CMN(__nv_bfloat16, float); }
   else { if (out_bf16) CMN(float, __nv_bfloat16); else CMN(float, float); }

@@ -104,6 +104,23 @@ def test_linear_fwd_bwd():
     assert rel_err(b.grad, br.grad) < 2e-2
 
 
+@pytest.mark.parametrize("B,I,O,relu", [(128, 2048, 1000, False), (64, 4096, 512, True)])
+def test_linear_small_batch_splitk_forward(B, I, O, relu):
+    """Small-batch FC forward: n-tiles x split-K into an fp32 scratch tile + the bias / ReLU / bf16 finishing kernel."""
+    torch.manual_seed(31)
+    x = torch.randn(B, I, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(O, I, device=DEV) * 0.03).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(O, device=DEV).requires_grad_(True)
+    y = ops.linear_bias_act(x, w, b, relu)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = x.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = ref.linear_bias_act(xr, wr, br, relu)
+    yr.backward(dy.float())
+    assert y.dtype == torch.bfloat16 and rel_err(y, yr) < 1e-2
+    assert rel_err(x.grad, xr.grad) < 2e-2 and rel_err(w.grad, wr.grad) < 2e-2 and rel_err(b.grad, br.grad) < 2e-2
+
+
 @pytest.mark.parametrize("cfg", [
     dict(N=4, H=31, W=31, C=3, O=32, k=11, s=4, p=0),      # conv1-like (C=3, K % 8 != 0)
     dict(N=3, H=13, W=13, C=64, O=96, k=3, s=1, p=1),

@@ -84,6 +84,7 @@ void device_barrier(const CommCtx& c, cudaStream_t st);
 void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, cudaStream_t st);
 void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, cudaStream_t st);
 void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, long long n, int max_blocks, cudaStream_t st);
+void bias_act_cast(const void* acc, const void* bias, void* y, int R, int C, int relu, cudaStream_t st);
 void cast_flat(const void* src, void* dst, long long n, int kind, cudaStream_t st);
 void sum_chunks(const void* src, void* dst, long long chunk, int nchunks, int is_half, cudaStream_t st);
 void vecadd(void* cur, const void* tmp, long long n, int is_half, cudaStream_t st);

@@ -111,6 +111,7 @@ PYBIND11_MODULE(_tmpi_native, m) {
     copy_flat(P(dst), P(dst_h), P(src), n, max_blocks, S(st)); });
   m.def("gosgd_merge", [](ptr_t w, ptr_t h, ptr_t b, float a_self, float a_src, long long n, int max_blocks, ptr_t st) {
     gosgd_merge(P(w), P(h), P(b), a_self, a_src, n, max_blocks, S(st)); });
+  m.def("bias_act_cast", [](ptr_t acc, ptr_t bias, ptr_t y, int R, int C, int relu, ptr_t st) { bias_act_cast(P(acc), P(bias), P(y), R, C, relu, S(st)); });
   m.def("cast_flat", [](ptr_t src, ptr_t dst, long long n, int kind, ptr_t st) { cast_flat(P(src), P(dst), n, kind, S(st)); });
   m.def("sum_chunks", [](ptr_t src, ptr_t dst, long long chunk, int nchunks, int is_half, ptr_t st) {
     sum_chunks(P(src), P(dst), chunk, nchunks, is_half, S(st)); });

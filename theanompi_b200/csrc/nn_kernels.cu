@@ -545,6 +545,34 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
   count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd"); ::tmpi::check_capture(st, "relu_bias_bwd");
 }
 
+// y[r, c] (bf16) = act(acc[r, c] (fp32) + bias[c]) — finishing pass of a split-K forward GEMM (small-batch FC layers: the
+// parallelism has to come from splitting K, and split-K accumulates in fp32 with reductions, so bias / ReLU / cast run here)
+__global__ void bias_act_cast_kernel(const float* __restrict__ acc, const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                     int R, int C, int relu) {
+  const int nvec = C >> 3;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (unsigned)R * (unsigned)nvec) return;
+  const unsigned r = idx / (unsigned)nvec; const int cv = (int)(idx - r * (unsigned)nvec);
+  const float4 a0 = *reinterpret_cast<const float4*>(acc + (size_t)r * C + cv * 8);
+  const float4 a1 = *reinterpret_cast<const float4*>(acc + (size_t)r * C + cv * 8 + 4);
+  float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  if (bias) {
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + cv * 8), b1 = *reinterpret_cast<const float4*>(bias + cv * 8 + 4);
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  *reinterpret_cast<bf16x8*>(y + (size_t)r * C + cv * 8) = pack8(v);
+}
+void bias_act_cast(const void* acc, const void* bias, void* y, int R, int C, int relu, cudaStream_t st) {
+  if (C % 8) throw std::runtime_error("bias_act_cast: C must be a multiple of 8");
+  const long long total = (long long)R * (C / 8);
+  bias_act_cast_kernel<<<grid_for(total, 256), 256, 0, st>>>((const float*)acc, (const float*)bias, (__nv_bfloat16*)y, R, C, relu);
+  count_launch(); TMPI_CHECK_LAUNCH("bias_act_cast"); ::tmpi::check_capture(st, "bias_act_cast");
+}
+
 // Fused backward of  conv(+bias+ReLU) -> max-pool : one pass over the conv output instead of three.
 //   dym[n,h,w,c] = (sum over pooling windows whose argmax is (h,w) of dyp) * (y[n,h,w,c] > 0)     (bf16, contiguous)
 //   db[c]       += sum_{n,h,w} dym                                                                 (pre-zeroed by the launcher)

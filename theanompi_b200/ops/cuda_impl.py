@@ -92,8 +92,16 @@ def linear_bias_act(x, w, b, relu=True):
     O = w.shape[0]
     xa, lda = _rows8(x2)
     wa, ldb = _rows8(_bf(w))
-    return gemm(xa, wa, B_, O, I, bias=b.float() if b is not None and b.dtype != torch.float32 else b,
-                bias_mode=1 if b is not None else 0, relu=relu, lda=lda, ldb=ldb)
+    bias = b.float() if b is not None and b.dtype != torch.float32 else b
+    if FC_SPLITK and B_ <= 128 and I >= 1024 and O % 8 == 0:
+        # small-batch FC forward is a weight stream: one m-tile, so the parallelism comes from n-tiles x split-K (fp32
+        # reductions into a scratch tile), followed by a tiny bias + ReLU + bf16 pass.  (The fused-epilogue kernel needs
+        # 32-wide tiles to fill the machine and then re-reads the activations 128 times through L2: 37 us vs 13 us for fc6.)
+        acc = gemm(xa, wa, B_, O, I, out_dtype=torch.float32, lda=lda, ldb=ldb)
+        y = torch.empty((B_, O), dtype=BF16, device=x2.device)
+        L().bias_act_cast(acc.data_ptr(), _p(bias), y.data_ptr(), int(B_), int(O), int(bool(relu)), _st(x2))
+        return y
+    return gemm(xa, wa, B_, O, I, bias=bias, bias_mode=1 if b is not None else 0, relu=relu, lda=lda, ldb=ldb)
 
 
 def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld):
@@ -192,6 +200,7 @@ def _w2d(w, K, Kp):
     return wp
 
 
+FC_SPLITK = os.environ.get("TMPI_FC_SPLITK", "1") != "0"      # small-batch FC forward: n-tiles x split-K + finishing pass
 CONV_MODE = os.environ.get("TMPI_CONV", "implicit")      # implicit: TMA-im2col implicit GEMM; explicit: im2col matrix + GEMM
 
 

@@ -137,6 +137,7 @@ __global__ void maxpool_relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ d
 template <int K>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                           uint8_t* __restrict__ arg, PoolGeom g) {
+  const int k = K > 0 ? K : g.k;
   const int nvec = g.C >> 3;
   const int ho = blockIdx.x % g.Ho, n = blockIdx.x / g.Ho;
   const int h0 = ho * g.s - g.p;
@@ -146,42 +147,39 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* _
   for (int it = threadIdx.x; it < items; it += blockDim.x) {
     const int wo = it / nvec, cv = it - wo * nvec;
     const int w0 = wo * g.s - g.p;
-    float best[8]; int bi[8];
+    // running max and its window index stay PACKED (two bf16 / two 16-bit indices per register): one __hgt2_mask and two
+    // bit-selects per register and tap instead of unpack + compare + two selects per channel
+    uint32_t best[4], bidx[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
-    if (K > 0) {
+    for (int i = 0; i < 4; ++i) { best[i] = 0xFF80FF80u; bidx[i] = 0u; }          // -inf, index 0
 #pragma unroll
-      for (int kh = 0; kh < K; ++kh) {
-#pragma unroll
-        for (int kw = 0; kw < K; ++kw) {
-          const int h = h0 + kh, w = w0 + kw;
-          if (h >= 0 && h < g.H && w >= 0 && w < g.W) {
-            float v[8];
-            unpack8(*reinterpret_cast<const bf16x8*>(xin + ((unsigned)(h * g.W + w) * (unsigned)g.C + cv * 8)), v);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * K + kw; }
-          }
-        }
-      }
-    } else {
-      for (int kh = 0; kh < g.k; ++kh) {
-        const int h = h0 + kh;
+    for (int kh = 0; kh < (K > 0 ? K : 1); ++kh) {
+      for (int kh2 = (K > 0 ? kh : 0); kh2 < (K > 0 ? kh + 1 : k); ++kh2) {
+        const int h = h0 + kh2;
         if (h < 0 || h >= g.H) continue;
-        for (int kw = 0; kw < g.k; ++kw) {
-          const int w = w0 + kw;
-          if (w < 0 || w >= g.W) continue;
-          float v[8];
-          unpack8(*reinterpret_cast<const bf16x8*>(xin + ((unsigned)(h * g.W + w) * (unsigned)g.C + cv * 8)), v);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; bi[i] = kh * g.k + kw; }
+        for (int kw = 0; kw < (K > 0 ? K : 1); ++kw) {
+          for (int kw2 = (K > 0 ? kw : 0); kw2 < (K > 0 ? kw + 1 : k); ++kw2) {
+            const int w = w0 + kw2;
+            if (w < 0 || w >= g.W) continue;
+            const bf16x8 v = *reinterpret_cast<const bf16x8*>(xin + ((unsigned)(h * g.W + w) * (unsigned)g.C + cv * 8));
+            const uint32_t* vw = reinterpret_cast<const uint32_t*>(&v);
+            const uint32_t tt = (uint32_t)(kh2 * k + kw2) * 0x00010001u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t m = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&vw[i]), *reinterpret_cast<const __nv_bfloat162*>(&best[i]));
+              best[i] = (vw[i] & m) | (best[i] & ~m);
+              bidx[i] = (tt & m) | (bidx[i] & ~m);
+            }
+          }
         }
       }
     }
     const long long o = orow + (unsigned)(wo * g.C + cv * 8);
-    *reinterpret_cast<bf16x8*>(y + o) = pack8(best);
-    uint2 packed;
-    packed.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-    packed.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+    *reinterpret_cast<uint4*>(y + o) = make_uint4(best[0], best[1], best[2], best[3]);
+    uint2 packed;                                   // 8 window indices, one byte per channel
+    packed.x = __byte_perm(bidx[0], bidx[1], 0x6420);
+    packed.y = __byte_perm(bidx[2], bidx[3], 0x6420);
     *reinterpret_cast<uint2*>(arg + o) = packed;
   }
 }

@@ -50,6 +50,12 @@ void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, i
                      int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st);
 void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
                      int Wo, int S, int P, int O, long long ldy, cudaStream_t st);
+// both groups of a 2-group convolution in one persistent launch (see gemm_tcgen05.cu)
+void conv_fprop2_bf16(const void* x, const void* w0, const void* w1, void* y0, void* y1, const float* bias0, const float* bias1, int N, int H,
+                      int W, int Ctot, int c_off0, int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
+                      int relu, int out_bf16, int dgrad, cudaStream_t st);
+void conv_wgrad2_bf16(const void* dy0, const void* dy1, const void* x, void* dw0, void* dw1, int N, int H, int W, int Ctot, int c_off0,
+                      int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st);
 
 // ---- nn_kernels.cu
 void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st);
@@ -64,6 +70,8 @@ void dropout_bwd(const void* dy, const void* mask, void* dx, long long n, cudaSt
 void advance_step(void* step, cudaStream_t st);
 void softmax_xent(const void* logits, const void* labels, void* dlogits, void* rowstat, void* out3, int B, int C, float weight, cudaStream_t st);
 void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st);
+void relu_bias_bwd2(const void* dy, const void* y, void* dym, void* db, void* db1, int c_split, long long R, int C, long long ld, int relu,
+                    cudaStream_t st);
 void maxpool_relu_bias_bwd(const void* dyp, const void* arg, const void* y, void* dym, void* db0, void* db1, int c_split, int N, int H,
                            int W, int C, int Ho, int Wo, int k, int s, int p, cudaStream_t st);
 void im2col(const void* x, void* col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,

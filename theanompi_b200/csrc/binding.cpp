@@ -63,6 +63,15 @@ PYBIND11_MODULE(_tmpi_native, m) {
                          int Pd, int O, long long ldy, ptr_t st) {
     conv_wgrad_bf16(P(dy), P(x), P(dw), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, S, Pd, O, ldy, S_(st));
   });
+  m.def("conv_fprop2", [](ptr_t x, ptr_t w0, ptr_t w1, ptr_t y0, ptr_t y1, ptr_t b0, ptr_t b1, int N, int H, int W, int Ctot, int c_off0, int c_off1,
+                          int Cg, int KH, int KW, int Ho, int Wo, int S, int Pd, int O, long long ldc, int relu, int out_bf16, int dgrad, ptr_t st) {
+    conv_fprop2_bf16(P(x), P(w0), P(w1), P(y0), P(y1), (const float*)P(b0), (const float*)P(b1), N, H, W, Ctot, c_off0, c_off1, Cg, KH, KW, Ho,
+                     Wo, S, Pd, O, ldc, relu, out_bf16, dgrad, S_(st));
+  });
+  m.def("conv_wgrad2", [](ptr_t dy0, ptr_t dy1, ptr_t x, ptr_t dw0, ptr_t dw1, int N, int H, int W, int Ctot, int c_off0, int c_off1, int Cg,
+                          int KH, int KW, int Ho, int Wo, int S, int Pd, int O, long long ldy, ptr_t st) {
+    conv_wgrad2_bf16(P(dy0), P(dy1), P(x), P(dw0), P(dw1), N, H, W, Ctot, c_off0, c_off1, Cg, KH, KW, Ho, Wo, S, Pd, O, ldy, S_(st));
+  });
   m.def("space_to_depth", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, ptr_t st) {
     space_to_depth(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, S_(st)); });
   m.def("s2d_filter", [](ptr_t src, ptr_t dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, ptr_t st) {
@@ -87,6 +96,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.def("maxpool_relu_bias_bwd", [](ptr_t dyp, ptr_t arg, ptr_t y, ptr_t dym, ptr_t db0, ptr_t db1, int c_split, int N, int H, int W, int C,
                                     int Ho, int Wo, int k, int s, int p, ptr_t st) {
     maxpool_relu_bias_bwd(P(dyp), P(arg), P(y), P(dym), P(db0), P(db1), c_split, N, H, W, C, Ho, Wo, k, s, p, S(st)); });
+  m.def("relu_bias_bwd2", [](ptr_t dy, ptr_t y, ptr_t dym, ptr_t db, ptr_t db1, int c_split, long long R, int C, long long ld, int relu, ptr_t st) {
+    relu_bias_bwd2(P(dy), P(y), P(dym), P(db), P(db1), c_split, R, C, ld, relu, S(st)); });
   m.def("relu_bias_bwd", [](ptr_t dy, ptr_t y, ptr_t dym, ptr_t db, long long R, int C, long long ld, int relu, ptr_t st) {
     relu_bias_bwd(P(dy), P(y), P(dym), P(db), R, C, ld, relu, S(st)); });
   m.def("im2col", [](ptr_t x, ptr_t col, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,

@@ -72,6 +72,11 @@ struct Params {
   int conv_mode;
   int cHo, cWo, cS, cP, cKH, cKW, cCg, c_chunks;
   int atomic_out;       // 1 = fp32 atomicAdd (split-K)
+  // second problem of the same shape run by the same launch (the two groups of an AlexNet-style grouped convolution): tiles
+  // [0, per_group) belong to group 0 (maps a/b, C, bias), tiles [per_group, 2*per_group) to group 1 (maps a1/b1, C1, bias1)
+  void* C1;
+  const float* bias1;
+  int groups;           // 1 or 2
   int group_m;          // tile raster: m-tiles per band (0 = plain m-fastest order); see tile_mn()
   int dbg;              // bottleneck probe (scripts/gemm_probe.py): 1 = skip A loads, 2 = skip B loads, 4 = skip the MMAs
 };
@@ -218,7 +223,8 @@ __device__ __forceinline__ void tile_mn(const Params& p, int rem, int& mti, int&
 // descriptor fetch) is paid once per SM instead of once per tile.
 template <int BN, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_b0,
+                  const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b1, const Params p) {
   using C = Cfg<BN, MT>;
   constexpr int TM = MT * BM;                      // rows of a CTA tile
   extern __shared__ uint8_t smem_raw[];
@@ -236,11 +242,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int lane = threadIdx.x & 31;
   const int num_kb_total = p.num_kb;
   const int tiles_mn = p.mt * p.nt;
-  const int total_tiles = tiles_mn * p.splits;
+  const int per_group = tiles_mn * p.splits;
+  const int total_tiles = per_group * p.groups;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_a0);
+    tma_prefetch_desc(&tmap_b0);
+    if (p.groups > 1) { tma_prefetch_desc(&tmap_a1); tma_prefetch_desc(&tmap_b1); }
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < C::ACC_STAGES; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), NUM_EPI_WARPS); }
     fence_barrier_init();
@@ -263,7 +271,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool issue_a = leader && !skip_a, issue_b = leader && !skip_b;
     int stage = 0; uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int split = tile / tiles_mn, rem = tile - split * tiles_mn;
+      const int grp = tile >= per_group ? 1 : 0;
+      const int t2 = tile - grp * per_group;
+      const CUtensorMap* const tma_a = grp ? &tmap_a1 : &tmap_a0;
+      const CUtensorMap* const tma_b = grp ? &tmap_b1 : &tmap_b0;
+      const int split = t2 / tiles_mn, rem = t2 - split * tiles_mn;
       int mti, nti;
       tile_mn(p, rem, mti, nti);
       const int m0 = mti * TM, n0 = nti * BN;
@@ -293,17 +305,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (issue_a) {
 #pragma unroll
             for (int u = 0; u < MT; ++u)
-              if (u < n_sub) tma_load_im2col(sa + u * (BM * BK * 2), &tmap_a, fb, cc * BK, bw0[u], bh0[u], img0[u], s_, r_);
+              if (u < n_sub) tma_load_im2col(sa + u * (BM * BK * 2), tma_a, fb, cc * BK, bw0[u], bh0[u], img0[u], s_, r_);
           }
           if (issue_b) {
             if (!b_t) {
-              tma_load_3d(sa + C::A_BYTES, &tmap_b, fb, cc * BK, tap, n0);            // weights [n][tap][k]: K-major box
+              tma_load_3d(sa + C::A_BYTES, tma_b, fb, cc * BK, tap, n0);            // weights [n][tap][k]: K-major box
             } else {
               // dgrad reads the FORWARD filter [k = out-ch][tap][n = in-ch] in place: MN-major boxes {64 n, 1 tap, 64 k} of
               // the mirrored tap (no flipped / transposed copy of the weights)
 #pragma unroll
               for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-                tma_load_3d(sa + C::A_BYTES + j * (BK * 128), &tmap_b, fb, n0 + 64 * j, ntaps - 1 - tap, cc * BK);
+                tma_load_3d(sa + C::A_BYTES + j * (BK * 128), tma_b, fb, n0 + 64 * j, ntaps - 1 - tap, cc * BK);
             }
           }
           if (++cc == p.c_chunks) { cc = 0; ++tap; if (++s_ == p.cKW) { s_ = 0; ++r_; } }
@@ -337,13 +349,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (leader) mbar_expect_tx(fb, tx);
           if (issue_a) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), &tmap_a, fb, m0 + 64 * j, pix);
+            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, fb, m0 + 64 * j, pix);
           }
           if (issue_b) {
             const int cw = qq * p.cS - p.cP, ch = pp * p.cS - p.cP;
 #pragma unroll
             for (int j = 0; j < NBOX; ++j)
-              if (j < nbox) tma_load_im2col(sb + j * (BK * 128), &tmap_b, fb, bc[j], cw, ch, img, bs[j], br[j]);
+              if (j < nbox) tma_load_im2col(sb + j * (BK * 128), tma_b, fb, bc[j], cw, ch, img, bs[j], br[j]);
           }
           pix += BK; qq += BK;
           while (qq >= p.cWo) { qq -= p.cWo; if (++pp == p.cHo) { pp = 0; ++img; } }
@@ -365,20 +377,20 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (int u = 0; u < MT; ++u) {
               if (u < n_sub) {
                 if (!a_mn) {
-                  tma_load_2d(sa + u * (BM * BK * 2), &tmap_a, fb, k0, m0 + u * BM);
+                  tma_load_2d(sa + u * (BM * BK * 2), tma_a, fb, k0, m0 + u * BM);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + u * (BM * BK * 2) + j * (BK * 128), &tmap_a, fb, m0 + u * BM + 64 * j, k0);
+                  for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + u * (BM * BK * 2) + j * (BK * 128), tma_a, fb, m0 + u * BM + 64 * j, k0);
                 }
               }
             }
           }
           if (issue_b) {
             if (!b_mn) {
-              tma_load_2d(sb, &tmap_b, fb, k0, n0);
+              tma_load_2d(sb, tma_b, fb, k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) tma_load_2d(sb + j * (BK * 128), &tmap_b, fb, n0 + 64 * j, k0);
+              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) tma_load_2d(sb + j * (BK * 128), tma_b, fb, n0 + 64 * j, k0);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -403,7 +415,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     int stage = 0; uint32_t phase = 0;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int split = tile / tiles_mn;
+      const int t2 = tile >= per_group ? tile - per_group : tile;
+      const int split = t2 / tiles_mn;
       const int kb0 = split * p.kb_per_split, kb1 = min(num_kb_total, kb0 + p.kb_per_split);
       const int acc = t & 1;
       mbar_wait(tmem_empty_bar(acc), (uint32_t)(((t >> 1) & 1) ^ 1));       // epilogue drained this accumulator
@@ -454,7 +467,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const bool ld_ok = (((long long)p.ldc * esz) % 16) == 0;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int rem = tile % tiles_mn;
+      const int grp = tile >= per_group ? 1 : 0;
+      const int rem = (tile - grp * per_group) % tiles_mn;
+      uint8_t* const Cg_ptr = reinterpret_cast<uint8_t*>(grp ? p.C1 : p.C);
+      const float* const bias_ptr = grp ? p.bias1 : p.bias;
       int mti, nti;
       tile_mn(p, rem, mti, nti);
       const int m0 = mti * TM;
@@ -475,14 +491,14 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       // bias of column (chunk base + j), broadcast later with shuffles; per-row bias — one value per sub-tile row.
       float bias_m0 = 0.f, bias_m1 = 0.f;
       if (p.bias_mode == 2) {
-        if (m0 + row < p.M) bias_m0 = __ldg(p.bias + m0 + row);
-        if (MT == 2 && m0 + BM + row < p.M) bias_m1 = __ldg(p.bias + m0 + BM + row);
+        if (m0 + row < p.M) bias_m0 = __ldg(bias_ptr + m0 + row);
+        if (MT == 2 && m0 + BM + row < p.M) bias_m1 = __ldg(bias_ptr + m0 + BM + row);
       }
       float bias_c0 = 0.f, bias_c1 = 0.f;
       if (p.bias_mode == 1 && active) {
         const int cb = n0 + col0 + lane;
-        if (cb < n_end) bias_c0 = __ldg(p.bias + cb);
-        if (NCHUNK > 1 && cb + 32 < n_end) bias_c1 = __ldg(p.bias + cb + 32);
+        if (cb < n_end) bias_c0 = __ldg(bias_ptr + cb);
+        if (NCHUNK > 1 && cb + 32 < n_end) bias_c1 = __ldg(bias_ptr + cb + 32);
       }
       const int acc = t & 1;
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc * C::ACC_COLS);
@@ -529,7 +545,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           }
           // Fast path: chunk fully in range and 16-byte aligned → transposed through smem, coalesced 16 B row-segment
           // stores (plain, or vector reductions red.global.add.v4.f32 for split-K).
-          const bool staged = (nb + 32 <= n_end) && ld_ok && (((reinterpret_cast<uintptr_t>(p.C) + (long long)nb * esz) % 16) == 0);
+          const bool staged = (nb + 32 <= n_end) && ld_ok && (((reinterpret_cast<uintptr_t>(Cg_ptr) + (long long)nb * esz) % 16) == 0);
           if (staged) {
             uint8_t* dst = wstage + (size_t)lane * pitch;
             if (p.out_bf16) {
@@ -540,7 +556,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
             __syncwarp();
-            uint8_t* gbase = reinterpret_cast<uint8_t*>(p.C) + (long long)nb * esz + (long long)lv * 16;
+            uint8_t* gbase = Cg_ptr + (long long)nb * esz + (long long)lv * 16;
             for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
               const int rr = r0 + lr;                                  // row inside this warp's 32-row band
               const long long gm = (long long)mbase + 32 * q + rr;
@@ -561,11 +577,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (!m_ok || nb >= n_end) continue;
           const bool full = (nb + 32 <= n_end);
           if (p.atomic_out) {
-            float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+            float* dst = reinterpret_cast<float*>(Cg_ptr) + (long long)m * p.ldc + nb;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
           } else if (p.out_bf16) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)m * p.ldc + nb;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cg_ptr) + (long long)m * p.ldc + nb;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
@@ -574,7 +590,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = f_to_bf16(v[j]);
             }
           } else {
-            float* dst = reinterpret_cast<float*>(p.C) + (long long)m * p.ldc + nb;
+            float* dst = reinterpret_cast<float*>(Cg_ptr) + (long long)m * p.ldc + nb;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -658,18 +674,20 @@ static int choose_splits(int tiles, int num_kb, int sms) {
 }
 
 template <int BN, int MT>
-static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st) {
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st,
+                   const CUtensorMap* ta1 = nullptr, const CUtensorMap* tb1 = nullptr) {
   using C = Cfg<BN, MT>;
   p.dbg = g_dbg;
+  if (!ta1) { p.groups = 1; p.C1 = nullptr; p.bias1 = nullptr; }
   static bool attr_set = false;
   if (!attr_set) {
     check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
     attr_set = true;
   }
   if (MT == 2 && !p.out_bf16) throw std::runtime_error("tmpi_native: 256-row GEMM tiles are bf16-output only");
-  const long long total = (long long)p.mt * p.nt * splits;
+  const long long total = (long long)p.mt * p.nt * splits * p.groups;
   const int grid = (int)std::min<long long>(total, (long long)sm_count());
-  gemm_bf16_tcgen05<BN, MT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_bf16_tcgen05<BN, MT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, p);
   count_launch();
   TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
 }
@@ -814,33 +832,57 @@ static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int b
 // y[N*Ho*Wo, O] (ld = ldc, bf16) = relu(conv(x[.., c_off:c_off+Cg], w[O][KH][KW][Cg]) + bias)   — no col matrix in memory
 // dgrad = 1: the same kernel computes the input gradient — x is dy, (Cg, O) are (#dy channels, #dx channels) and w is the
 // FORWARD filter [Cg][KH][KW][O], read mirrored and transposed by the TMA loads (stride-1 convolutions only).
-void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
-                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st) {
+// ngroups = 2: both groups of a grouped convolution in ONE persistent launch (group g reads channel slice c_off[g] of x,
+// filter w[g], writes y[g] / adds bias[g]) — their tiles fill the machine together instead of two under-filled waves.
+static void conv_fprop_groups(int ngroups, const void* x, const int* c_off, const void* const* w, void* const* y, const float* const* bias,
+                              int N, int H, int W, int Ctot, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
+                              int relu, int out_bf16, int dgrad, cudaStream_t st) {
   using namespace gemm;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0 || O <= 0) return;
   if (M >= (1LL << 31)) throw std::runtime_error("conv_fprop: too many output pixels");
   const int BN = O > 64 ? 128 : 64;
   Params p;
-  p.C = y; p.bias = bias; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = dgrad ? 1 : 0;
-  p.out_bf16 = out_bf16; p.bias_mode = bias ? 1 : 0; p.relu = relu; p.atomic_out = 0;
+  p.C = y[0]; p.bias = bias[0]; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = dgrad ? 1 : 0;
+  p.groups = ngroups; p.C1 = ngroups > 1 ? y[1] : nullptr; p.bias1 = ngroups > 1 ? bias[1] : nullptr;
+  p.out_bf16 = out_bf16; p.bias_mode = bias[0] ? 1 : 0; p.relu = relu; p.atomic_out = 0;
+  if (ngroups > 1 && ((bias[0] == nullptr) != (bias[1] == nullptr))) throw std::runtime_error("conv_fprop: both groups need a bias or none");
   if (dgrad && (S != 1 || (O % 8) != 0)) throw std::runtime_error("conv dgrad through the fprop kernel needs stride 1 and C % 8 == 0");
   p.nt = (O + BN - 1) / BN; p.splits = 1;
-  const bool tall = use_tall_tiles(M, p.nt, out_bf16, sm_count());
+  const bool tall = use_tall_tiles(M, p.nt * ngroups, out_bf16, sm_count());
   p.mt = tall ? (int)((M + 2 * BM - 1) / (2 * BM)) : (int)((M + BM - 1) / BM);
   p.group_m = 0;
   p.conv_mode = 1; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BK - 1) / BK;
   p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
-  CUtensorMap ta = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BM);
-  CUtensorMap tb = dgrad ? make_weight_map(w, Cg, KH * KW, O, 64, 64) : make_weight_map(w, O, KH * KW, Cg, BN);
-  if (tall) { if (BN == 128) launch<128, 2>(ta, tb, p, 1, st); else launch<64, 2>(ta, tb, p, 1, st); }
-  else if (BN == 128) launch<128, 1>(ta, tb, p, 1, st);
-  else launch<64, 1>(ta, tb, p, 1, st);
+  CUtensorMap ta[2], tb[2];
+  for (int g = 0; g < ngroups; ++g) {
+    ta[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BM);
+    tb[g] = dgrad ? make_weight_map(w[g], Cg, KH * KW, O, 64, 64) : make_weight_map(w[g], O, KH * KW, Cg, BN);
+  }
+  const CUtensorMap* a1 = ngroups > 1 ? &ta[1] : nullptr;
+  const CUtensorMap* b1 = ngroups > 1 ? &tb[1] : nullptr;
+  if (tall) { if (BN == 128) launch<128, 2>(ta[0], tb[0], p, 1, st, a1, b1); else launch<64, 2>(ta[0], tb[0], p, 1, st, a1, b1); }
+  else if (BN == 128) launch<128, 1>(ta[0], tb[0], p, 1, st, a1, b1);
+  else launch<64, 1>(ta[0], tb[0], p, 1, st, a1, b1);
+}
+
+void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st) {
+  const void* ws[1] = {w}; void* ys[1] = {y}; const float* bs[1] = {bias};
+  conv_fprop_groups(1, x, &c_off, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
+}
+
+void conv_fprop2_bf16(const void* x, const void* w0, const void* w1, void* y0, void* y1, const float* bias0, const float* bias1, int N, int H,
+                      int W, int Ctot, int c_off0, int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
+                      int relu, int out_bf16, int dgrad, cudaStream_t st) {
+  const int co[2] = {c_off0, c_off1}; const void* ws[2] = {w0, w1}; void* ys[2] = {y0, y1}; const float* bs[2] = {bias0, bias1};
+  conv_fprop_groups(2, x, co, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
 }
 
 // dw[O][KH*KW][Cg] (fp32, contiguous) = sum over pixels dy[pix, o] * im2col(x)[pix, (tap, c)]   (dy: [M, O] bf16, row pitch ldy)
-void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
-                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+// ngroups = 2: both groups in one launch (dy[g] = the group's channel slice of the output gradient, x slice c_off[g], dw[g]).
+static void conv_wgrad_groups(int ngroups, const void* const* dy, const void* x, void* const* dw, const int* c_off, int N, int H, int W,
+                              int Ctot, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
   using namespace gemm;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0 || O <= 0) return;
@@ -848,20 +890,36 @@ void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int 
   const int sms = sm_count();
   const int BN = 128;                                  // two (tap, 64-channel) boxes per n-tile: halves the re-reads of dy
   Params p;
-  p.C = dw; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
+  p.C = dw[0]; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
+  p.groups = ngroups; p.C1 = ngroups > 1 ? dw[1] : nullptr; p.bias1 = nullptr;
   p.out_bf16 = 0; p.bias_mode = 0; p.relu = 0;
   p.group_m = 0;
   p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + 63) / 64;
   p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / 64 - 1) / (BN / 64);
   p.num_kb = (int)((M + BK - 1) / BK);
-  int splits = choose_splits(p.mt * p.nt, p.num_kb, sms);
+  int splits = choose_splits(p.mt * p.nt * ngroups, p.num_kb, sms);
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
   splits = (p.num_kb + p.kb_per_split - 1) / p.kb_per_split;
   p.splits = splits; p.atomic_out = splits > 1;
-  if (splits > 1) check_cuda(cudaMemsetAsync(dw, 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
-  CUtensorMap ta = make_tmap(dy, (uint64_t)O, (uint64_t)M, (uint64_t)ldy * 2, 64u);
-  CUtensorMap tb = make_im2col_map(x, N, H, W, Ctot, c_off, Cg, KH, KW, S, P, BK);
-  if (BN == 128) launch<128, 1>(ta, tb, p, splits, st); else launch<64, 1>(ta, tb, p, splits, st);
+  CUtensorMap ta[2], tb[2];
+  for (int g = 0; g < ngroups; ++g) {
+    if (splits > 1) check_cuda(cudaMemsetAsync(dw[g], 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
+    ta[g] = make_tmap(dy[g], (uint64_t)O, (uint64_t)M, (uint64_t)ldy * 2, 64u);
+    tb[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BK);
+  }
+  launch<128, 1>(ta[0], tb[0], p, splits, st, ngroups > 1 ? &ta[1] : nullptr, ngroups > 1 ? &tb[1] : nullptr);
+}
+
+void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
+                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+  const void* dys[1] = {dy}; void* dws[1] = {dw};
+  conv_wgrad_groups(1, dys, x, dws, &c_off, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
+}
+
+void conv_wgrad2_bf16(const void* dy0, const void* dy1, const void* x, void* dw0, void* dw1, int N, int H, int W, int Ctot, int c_off0,
+                      int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+  const void* dys[2] = {dy0, dy1}; void* dws[2] = {dw0, dw1}; const int co[2] = {c_off0, c_off1};
+  conv_wgrad_groups(2, dys, x, dws, co, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
 }
 
 }  // namespace tmpi

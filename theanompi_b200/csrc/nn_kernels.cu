@@ -465,8 +465,8 @@ void softmax_xent(const void* logits, const void* labels, void* dlogits, void* r
 // dy / y have row pitch ld (elements) so channel slices of a wider tensor work (grouped conv).
 template <bool RELU, bool WRITE>
 __global__ void relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
-                                     __nv_bfloat16* __restrict__ dym, float* __restrict__ db, long long R, int C,
-                                     long long ld, int VT, int rows_per_cta) {
+                                     __nv_bfloat16* __restrict__ dym, float* __restrict__ db, float* __restrict__ db1, int c_split,
+                                     long long R, int C, long long ld, int VT, int rows_per_cta) {
   extern __shared__ float sm[];                       // [RL][VT*8]
   const int nvec = C >> 3;
   const int RL = blockDim.x / VT;
@@ -520,12 +520,15 @@ __global__ void relu_bias_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
     if (c < C) {
       float s = 0.f;
       for (int t = 0; t < RL; ++t) s += sm[(t * VT + v) * 8 + i];
-      atomicAdd(db + c, s);
+      atomicAdd(c < c_split ? db + c : db1 + (c - c_split), s);
     }
   }
 }
 
-void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st) {
+// db: bias gradient for channels [0, c_split), db1: for channels [c_split, C) (the two parameter sets of a 2-group block);
+// pass db1 = nullptr / c_split = C for a single bias vector.
+void relu_bias_bwd2(const void* dy, const void* y, void* dym, void* db, void* db1, int c_split, long long R, int C, long long ld, int relu,
+                    cudaStream_t st) {
   if (C % 8) throw std::runtime_error("relu_bias_bwd: C must be a multiple of 8");
   const int nvec = C / 8;
   const int VT = nvec < 32 ? nvec : 32;
@@ -533,14 +536,19 @@ void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long
   const int rows_per_cta = RL * 8;
   dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
-  if (db) check_cuda(cudaMemsetAsync(db, 0, (size_t)C * 4, st), "relu_bias_bwd memset");
+  if (!db1 || c_split > C) c_split = C;
+  if (db) check_cuda(cudaMemsetAsync(db, 0, (size_t)c_split * 4, st), "relu_bias_bwd memset");
+  if (db && c_split < C) check_cuda(cudaMemsetAsync(db1, 0, (size_t)(C - c_split) * 4, st), "relu_bias_bwd memset");
   const bool write = dym != nullptr;
-  auto DY = (const __nv_bfloat16*)dy; auto Y = (const __nv_bfloat16*)y; auto DM = (__nv_bfloat16*)dym; auto DB = (float*)db;
-  if (relu && write) relu_bias_bwd_kernel<true, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
-  else if (relu) relu_bias_bwd_kernel<true, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
-  else if (write) relu_bias_bwd_kernel<false, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
-  else relu_bias_bwd_kernel<false, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, R, C, ld, VT, rows_per_cta);
+  auto DY = (const __nv_bfloat16*)dy; auto Y = (const __nv_bfloat16*)y; auto DM = (__nv_bfloat16*)dym; auto DB = (float*)db; auto DB1 = (float*)db1;
+  if (relu && write) relu_bias_bwd_kernel<true, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, DB1, c_split, R, C, ld, VT, rows_per_cta);
+  else if (relu) relu_bias_bwd_kernel<true, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, DB1, c_split, R, C, ld, VT, rows_per_cta);
+  else if (write) relu_bias_bwd_kernel<false, true><<<grid, 256, smem, st>>>(DY, Y, DM, DB, DB1, c_split, R, C, ld, VT, rows_per_cta);
+  else relu_bias_bwd_kernel<false, false><<<grid, 256, smem, st>>>(DY, Y, DM, DB, DB1, c_split, R, C, ld, VT, rows_per_cta);
   count_launch(); TMPI_CHECK_LAUNCH("relu_bias_bwd"); ::tmpi::check_capture(st, "relu_bias_bwd");
+}
+void relu_bias_bwd(const void* dy, const void* y, void* dym, void* db, long long R, int C, long long ld, int relu, cudaStream_t st) {
+  relu_bias_bwd2(dy, y, dym, db, nullptr, C, R, C, ld, relu, st);
 }
 
 // y[r, c] (bf16) = act(acc[r, c] (fp32) + bias[c]) — finishing pass of a split-K forward GEMM (small-batch FC layers: the

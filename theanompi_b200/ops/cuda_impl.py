@@ -200,6 +200,7 @@ def _w2d(w, K, Kp):
     return wp
 
 
+GROUP2_FUSED = os.environ.get("TMPI_GROUP2_FUSED", "1") != "0"   # both groups of a 2-group conv per launch
 FC_SPLITK = os.environ.get("TMPI_FC_SPLITK", "1") != "0"      # small-batch FC forward: n-tiles x split-K + finishing pass
 CONV_MODE = os.environ.get("TMPI_CONV", "implicit")      # implicit: TMA-im2col implicit GEMM; explicit: im2col matrix + GEMM
 
@@ -303,6 +304,12 @@ def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu, return_cols=Fal
     Og, KH, KW, Cg = w0.shape
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
     y = torch.empty((N, Ho, Wo, 2 * Og), dtype=BF16, device=x.device)
+    wb0, wb1 = _bf(w0), _bf(w1)
+    if GROUP2_FUSED and _implicit_ok(x, wb0, 0, Cg, 2 * Og, 0) and _implicit_ok(x, wb1, Cg, Cg, 2 * Og, Og) and (b0 is None) == (b1 is None):
+        # both groups in ONE persistent launch: their tiles fill the 148 SMs together instead of two under-filled waves
+        L().conv_fprop2(x.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), y.data_ptr(), y.data_ptr() + Og * 2, _p(b0), _p(b1), N, H, W, C, 0,
+                        int(Cg), int(Cg), KH, KW, Ho, Wo, int(stride), int(pad), Og, 2 * Og, int(bool(relu)), 1, 0, _st(x))
+        return (y, [None, None]) if return_cols else y
     cols = [_conv_fwd_group(x, w0, b0, y, 0, 0, Cg, stride, pad, relu),
             _conv_fwd_group(x, w1, b1, y, Og, Cg, Cg, stride, pad, relu)]
     return (y, cols) if return_cols else y
@@ -389,6 +396,32 @@ def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, out
     dy = _bf(dy).contiguous()
     Og, KH, KW, Cg = w0.shape
     dx = torch.empty_like(x) if need_dx else None
+    wb0, wb1 = _bf(w0), _bf(w1)
+    Ot = 2 * Og
+    no_cols = not cols or (cols[0] is None and cols[1] is None)
+    if (GROUP2_FUSED and no_cols and _implicit_ok(x, wb0, 0, Cg, Ot, 0) and _implicit_ok(x, wb1, Cg, Cg, Ot, Og)
+            and (not need_dx or stride == 1)):
+        # ---- both groups per launch: one mask/bias pass over the full width, one wgrad launch, one dgrad launch
+        N, H, W, Ct = x.shape
+        Ho, Wo = y.shape[1], y.shape[2]
+        M = N * Ho * Wo
+        dev = x.device
+        db0 = outs[1] if outs[1] is not None else torch.empty(Og, dtype=torch.float32, device=dev)
+        db1 = outs[3] if outs[3] is not None else torch.empty(Og, dtype=torch.float32, device=dev)
+        if pre_masked:
+            dym = dy
+        else:
+            dym = torch.empty((M, Ot), dtype=BF16, device=dev)
+            L().relu_bias_bwd2(dy.data_ptr(), y.data_ptr(), dym.data_ptr(), db0.data_ptr(), db1.data_ptr(), int(Og), int(M), int(Ot), int(Ot),
+                               int(bool(relu)), _st(x))
+        dw0 = outs[0] if outs[0] is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
+        dw1 = outs[2] if outs[2] is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
+        L().conv_wgrad2(dym.data_ptr(), dym.data_ptr() + Og * 2, x.data_ptr(), dw0.data_ptr(), dw1.data_ptr(), N, H, W, Ct, 0, int(Cg), int(Cg),
+                        KH, KW, Ho, Wo, int(stride), int(pad), Og, int(Ot), _st(x))
+        if need_dx:
+            L().conv_fprop2(dym.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), dx.data_ptr(), dx.data_ptr() + Cg * 2, 0, 0, N, Ho, Wo, int(Ot), 0,
+                            int(Og), int(Og), KH, KW, H, W, 1, KH - 1 - int(pad), int(Cg), Ct, 0, 1, 1, _st(x))
+        return dx, (dw0, db0, dw1, db1)
     dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1],
                                col=cols[0] if cols else None, pre_masked=pre_masked)
     dw1, db1 = _conv_bwd_group(x, w1, y, dy, dx, Og, Cg, Cg, stride, pad, relu, need_dx, outs[2], outs[3],

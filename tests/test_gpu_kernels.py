@@ -132,7 +132,7 @@ def test_linear_small_batch_splitk_forward(B, I, O, relu):
     dict(N=3, H=27, W=27, C=48, O=128, k=5, s=1, p=2),     # AlexNet conv2 group shape (C = 48)
     dict(N=40, H=13, W=13, C=256, O=384, k=3, s=1, p=1),   # many tiles + split-K wgrad
     dict(N=32, H=27, W=27, C=48, O=128, k=5, s=1, p=2),    # enough pixels for 256-row tiles in fprop and dgrad (BN = 64)
-    dict(N=37, H=13, W=13, C=192, O=192, k=3, s=1, p=1),   # 256-row tiles with a ragged last tile
+    dict(N=80, H=13, W=13, C=192, O=192, k=3, s=1, p=1),   # 256-row tiles with a ragged last tile
 ])
 def test_conv_fwd_bwd(cfg):
     torch.manual_seed(4)

@@ -692,12 +692,15 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int 
   TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
 }
 
-// 256-row tiles (MT = 2) when the output is bf16 (no split-K) and there are still enough tiles to fill the machine
+// 256-row tiles (MT = 2) when the output is bf16 (no split-K) and the wave arithmetic favours them: a tall tile costs ~1.7x a
+// 128-row tile (measured: conv3 fprop 21.5 us vs 12.8 us per wave — the B tile and the per-k-block overhead are shared), so
+// it wins unless halving the tile count wastes most of a wave (conv3 dgrad: 170 tall tiles = 2 waves vs 338 = 3 short ones).
 static bool use_tall_tiles(long long M, int nt, int out_bf16, int sms) {
   static const bool enabled = [] { const char* e = getenv("TMPI_GEMM_TALL"); return !(e && e[0] == '0'); }();
   if (!enabled || !out_bf16 || M < 2 * BM) return false;
-  const long long tiles = ((M + 2 * BM - 1) / (2 * BM)) * nt;
-  return tiles * 2 >= sms;
+  const long long t1 = ((M + BM - 1) / BM) * nt, t2 = ((M + 2 * BM - 1) / (2 * BM)) * nt;
+  const long long w1 = (t1 + sms - 1) / sms, w2 = (t2 + sms - 1) / sms;
+  return w2 * 17 <= w1 * 10;
 }
 
 }  // namespace gemm

@@ -1,10 +1,10 @@
 #!/bin/bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-nvidia-smi -L | head -3
-echo "=== kernel tests (1 GPU)"; timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x --tb=short --timeout 120 -p no:cacheprovider 2>&1 | tail -4
-echo "=== multigpu tests"; timeout 1200 python -m pytest tests/test_multigpu.py -m gpu -q -x --tb=short --timeout 600 -p no:cacheprovider 2>&1 | tail -25 | tee gpurun_out/t_multi2.log
-run() { name=$1; shift; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 40 --warmup 5 "$@" 2>&1 | grep '^{' | tail -1 | cut -c1-260 | tee gpurun_out/bench2_$name.log; }
-echo "=== bench N=2 default"; run default
-echo "=== bench N=2 no-overlap"; run noov --no-overlap
-echo "=== bench N=2 nccl32"; run nccl32 --strategy nccl32
+echo "=== easgd/gosgd rule tests"; timeout 700 python -m pytest tests/test_multigpu.py -m gpu -q --tb=short --timeout 300 -p no:cacheprovider -k "easgd or gosgd" 2>&1 | tail -40 | tee gpurun_out/t_multi2b.log
+run() { name=$1; shift; timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --steps 40 --warmup 5 "$@" 2>&1 | grep '^{' | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['config'].get('overlap'), d['config'].get('exch_strategy'))" | tee gpurun_out/bench2_$name.log; }
+echo "=== N=2 no-overlap"; run noov --no-overlap
+echo "=== N=2 overlap blocks 64"; TMPI_OVERLAP_BLOCKS=64 run ov64
+echo "=== N=2 overlap blocks 148"; TMPI_OVERLAP_BLOCKS=148 run ov148
+echo "=== N=2 overlap blocks 16"; TMPI_OVERLAP_BLOCKS=16 run ov16
+echo "=== N=2 fused16 no-overlap"; run f16 --no-overlap --strategy fused16

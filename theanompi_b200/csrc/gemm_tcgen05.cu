@@ -116,7 +116,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
       "@P1 bra DONE;\n\t"
       "add.u32 cnt, cnt, 1;\n\t"
-      "setp.lt.u32 P2, cnt, 0x1000000;\n\t"
+      "setp.lt.u32 P2, cnt, 0x10000000;\n\t"
       "@P2 bra LAB_WAIT;\n\t"
       "trap;\n\t"
       "DONE:\n\t"

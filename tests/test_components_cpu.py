@@ -291,3 +291,27 @@ def test_loader_handoff_identity_cpu():
     b1 = ld.get()
     assert b1.item == d.train_img[1]
     ld.drain(); d.para_load_close()
+
+
+def test_gemm_wave_planning_host_side():
+    """The launcher's wave arithmetic (host code of the native extension, no GPU needed): split-K factors must not spill a
+    few tiles into an extra wave, and 256-row tiles are only chosen when they do not waste most of a wave."""
+    from theanompi_b200.ops import native
+    L = native.lib()
+    if L is None:
+        pytest.skip("native extension not built")
+    sms = 148
+    # AlexNet conv2 wgrad: 13 tiles, 1458 k-blocks.  ceil(148 / 13) = 12 slices would be 156 CTAs → a 2nd wave for 8 tiles.
+    s = L.gemm_plan_splits(13, 1458, sms)
+    assert 13 * s <= sms and s == 11
+    # conv1 (space-to-depth) wgrad: 5 tiles, 6050 k-blocks → one full wave
+    s = L.gemm_plan_splits(5, 6050, sms)
+    assert 5 * s <= sms and 5 * (s + 1) > sms
+    assert L.gemm_plan_splits(200, 100, sms) == 1            # already more tiles than SMs
+    assert L.gemm_plan_splits(10, 4, sms) == 1               # too little K to split
+    # conv3 fprop (M = 21632, 3 n-tiles): 255 tall tiles = 2 waves beats 507 = 4 short waves
+    assert L.gemm_plan_tall(21632, 3, 1, sms) == 1
+    # conv3 dgrad (2 n-tiles): 170 tall tiles = 2 waves loses to 338 = 3 short waves
+    assert L.gemm_plan_tall(21632, 2, 1, sms) == 0
+    assert L.gemm_plan_tall(128, 32, 1, sms) == 0            # a single m-tile cannot be tall
+    assert L.gemm_plan_tall(8192, 64, 0, sms) == 0           # fp32 / split-K outputs never use tall tiles

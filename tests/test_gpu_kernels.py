@@ -158,10 +158,10 @@ def test_conv_fwd_bwd(cfg):
         assert rel_err(x.grad, dxr) < 2e-2
 
 
-@pytest.mark.parametrize("C,O", [(32, 64), (96, 256)])
-def test_conv_group2(C, O):
+@pytest.mark.parametrize("N,C,O", [(2, 32, 64), (2, 96, 256), (64, 96, 256)])    # the last: both groups in one launch of 256-row tiles
+def test_conv_group2(N, C, O):
     torch.manual_seed(5)
-    N, H, W = 2, 13, 13
+    H, W = 13, 13
     x = torch.randn(N, H, W, C, device=DEV).to(torch.bfloat16).requires_grad_(True)
     ws = [(torch.randn(O // 2, 3, 3, C // 2, device=DEV) * 0.1).to(torch.bfloat16).requires_grad_(True) for _ in range(2)]
     bs = [torch.randn(O // 2, device=DEV).requires_grad_(True) for _ in range(2)]

@@ -41,7 +41,9 @@ struct ReduceArgs {
 };
 
 // ---- gemm_tcgen05.cu
-void gemm_set_debug(int flags);   // bottleneck probe knobs of the tcgen05 GEMM (see Params::dbg)
+void gemm_set_debug(int flags);
+int gemm_plan_splits(int tiles, int num_kb, int sms);          // split-K factor the launcher would pick
+int gemm_plan_tall(long long M, int nt, int out_bf16, int sms);   // 1 = 256-row CTA tiles   // bottleneck probe knobs of the tcgen05 GEMM (see Params::dbg)
 void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
                long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
                cudaStream_t st);

@@ -707,6 +707,10 @@ static bool use_tall_tiles(long long M, int nt, int out_bf16, int sms) {
 
 void gemm_set_debug(int flags) { gemm::g_dbg = flags; }
 
+// host-side planning helpers, exported so the wave arithmetic can be unit-tested without a GPU
+int gemm_plan_splits(int tiles, int num_kb, int sms) { return gemm::choose_splits(tiles, num_kb, sms); }
+int gemm_plan_tall(long long M, int nt, int out_bf16, int sms) { return gemm::use_tall_tiles(M, nt, out_bf16, sms) ? 1 : 0; }
+
 // C[M,N] (ldc) = alpha * op(A) op(B) + bias, optional ReLU.
 //   a_mn == 0: A is [M, K] with row pitch lda (elements);  a_mn == 1: A is [K, M] with row pitch lda.
 //   b_mn == 0: B is [N, K] with row pitch ldb;             b_mn == 1: B is [K, N] with row pitch ldb.

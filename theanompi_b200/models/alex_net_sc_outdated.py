@@ -7,6 +7,7 @@ from .layers2 import Crop, Subtract, forward_chain
 
 
 class AlexNet_sc(AlexNet):
+    graph_safe = False            # the in-graph Crop layer draws offsets / mirrors from the host RNG every step
     def __init__(self, config):
         config = dict(config)
         config["no_paraload"] = True

@@ -60,6 +60,7 @@ class ModelBase(object):
     batch_crop_mirror = False
     rand_crop = True
     monitor_grad = False
+    graph_safe = True              # False: the step draws host-side randomness / has host control flow → never auto-capture
     name = "Model"
 
     def __init__(self, config):
@@ -71,7 +72,13 @@ class ModelBase(object):
         self.device = pick_device(config)
         self.cuda = self.device.type == "cuda"
         self.act_dtype = torch.bfloat16 if self.cuda else torch.float32
-        self.use_graph = bool(config.get("cuda_graph", False)) and self.cuda
+        # "auto" (default on CUDA): capture the whole step into a CUDA graph, fall back to eager launches if the model's
+        # step cannot be captured (host-side control flow, library calls that synchronise, …)
+        cg = config.get("cuda_graph", "auto")
+        self._graph_auto = (cg == "auto")
+        if self._graph_auto and not getattr(self, "graph_safe", True):
+            cg = False            # e.g. in-graph random crops drawn from a host RNG every step: a replay would freeze them
+        self.use_graph = bool(cg) and self.cuda
         self.epoch = 0
         self.step_idx = 0
         self.mu = self.momentum
@@ -175,7 +182,17 @@ class ModelBase(object):
                     out = self._step_body()
                 cur.wait_stream(self._gstream)
                 return out
-            self._capture()
+            try:
+                self._capture()
+            except Exception as e:  # noqa: BLE001
+                if not self._graph_auto:
+                    raise
+                print("[%s] CUDA-graph capture of the training step failed (%s: %s) — running eager"
+                      % (getattr(self, "name", type(self).__name__), type(e).__name__, str(e)[:200]))
+                self.use_graph = False
+                self._graph = None
+                torch.cuda.synchronize()
+                return self._step_body()
         self._graph.replay()
         return self._graph_out
 

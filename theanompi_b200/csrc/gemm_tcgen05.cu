@@ -1,18 +1,19 @@
-// Hand-written Blackwell GEMM:  C[M,N] = alpha * op(A) · op(B)  (+bias, +ReLU)  bf16 in, fp32 accumulate.
+// Hand-written Blackwell GEMM / implicit-GEMM convolution:  C[M,N] = alpha * op(A) · op(B)  (+bias, +ReLU), bf16 in, fp32 accumulate.
 //
-//   * operands staged global→shared by TMA (cp.async.bulk.tensor.2d, 128B swizzle),
-//   * tcgen05.mma.cta_group::1.kind::f16 issued by ONE thread, accumulator in TMEM,
-//   * mbarrier producer/consumer ring between the TMA warp and the MMA warp,
-//   * tcgen05.commit hands smem slots back / signals the epilogue,
-//   * 4 epilogue warps read TMEM with tcgen05.ld (32x32b.x32) and fuse bias / ReLU /
-//     bf16 cast / split-K reduction into the store.
+//   * persistent: one CTA per SM walks the tile list; 320 threads = warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer,
+//     warps 2..9 epilogue (warp % 4 selects the TMEM lane quarter it may read, (warp - 2) / 4 the column half);
+//   * operands staged global→shared by TMA (tiled 2-D / 3-D boxes or im2col-mode 4-D boxes, 128 B swizzle) into a 4–8 stage
+//     mbarrier ring; tcgen05.mma.cta_group::1.kind::f16 issued by one elected lane, accumulators in TMEM (2 stages, so the
+//     epilogue of tile i overlaps the main loop of tile i+1); tcgen05.commit hands smem slots back / signals the epilogue;
+//   * MT = 2: a CTA computes a 256-row tile as two MMAs per k-step against ONE B tile (bf16-output GEMMs with enough tiles);
+//   * epilogue: tcgen05.ld 32x32b.x32 → bias (prefetched, shuffle-broadcast) / ReLU → per-warp smem transpose of one
+//     32x32 chunk → coalesced 16 B row-segment stores, or red.global.add.v4.f32 for split-K;
+//   * two same-shape problems (the two groups of a grouped convolution) can share one launch.
 //
-// Both operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous):
-// forward, dgrad and wgrad of FC and (im2col) conv layers all run on this one kernel without any
-// transposed copies (reference: cuBLAS SGEMM through Theano, layers2.py:927-929, GpuCorrMM :597-653).
-//
-// Warp roles (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA issuer, warps2..5 = epilogue
-// (warp_id % 4 selects the TMEM lane quarter a warp may read).
+// Both operands may be K-major ([rows, K], K contiguous) or MN-major ([K, rows], rows contiguous): forward, dgrad and wgrad of
+// FC and conv layers all run on this one kernel without transposed copies (reference: cuBLAS SGEMM / cuDNN through Theano,
+// layers2.py:927-929, :380-388, GpuCorrMM :597-653).  What bounded the first versions and how it was found:
+// profiles/gemm_probe.md.
 #include "common.cuh"
 #include "api.h"
 #include <cuda.h>

@@ -315,3 +315,34 @@ def test_gemm_wave_planning_host_side():
     assert L.gemm_plan_tall(21632, 2, 1, sms) == 0
     assert L.gemm_plan_tall(128, 32, 1, sms) == 0            # a single m-tile cannot be tall
     assert L.gemm_plan_tall(8192, 64, 0, sms) == 0           # fp32 / split-K outputs never use tall tiles
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_conv_pool_block_single_node_equals_composition_cpu(groups):
+    """conv(+ReLU) with the pooling layer folded into the same autograd node (what ``ConvPoolLRN`` builds, so the CUDA
+    backward can fuse pool scatter + ReLU mask + bias gradient) == conv followed by ``pool2d`` — CPU reference path."""
+    from theanompi_b200 import ops
+    pool = (3, 2, 0, "max")
+
+    def make():
+        torch.manual_seed(3)
+        x = torch.randn(2, 13, 13, 8, requires_grad=True)
+        ws = [(torch.randn(6, 3, 3, 8 // groups) * 0.2).requires_grad_(True) for _ in range(groups)]
+        bs = [(torch.randn(6) * 0.1).requires_grad_(True) for _ in range(groups)]
+        return x, ws, bs
+
+    def run(fold):
+        x, ws, bs = make()
+        pl = pool if fold else None
+        if groups == 1:
+            y = ops.conv2d_bias_act(x, ws[0], bs[0], 1, 1, 1, True, pl)
+        else:
+            y = ops.conv2d_group2_bias_act(x, ws[0], bs[0], ws[1], bs[1], 1, 1, True, pl)
+        if not fold:
+            y = ops.pool2d(y, *pool)
+        torch.manual_seed(4)
+        y.backward(torch.randn_like(y))
+        return [y.detach(), x.grad] + [w.grad for w in ws] + [b.grad for b in bs]
+
+    for a, b in zip(run(True), run(False)):
+        assert torch.allclose(a, b, atol=1e-5), float((a - b).abs().max())

@@ -95,6 +95,46 @@ def main():
     assert torch.equal(arena.W[:b["lo"]], w0[:b["lo"]])
     assert not torch.equal(arena.W[b["lo"]:b["hi"]], w0[b["lo"]:b["hi"]])
 
+    # reduce-scatter fused into the wgrad GEMM epilogue: every rank's tcgen05 GEMM red.adds its dW tiles into the OWNER's G over
+    # NVLink; the exchange kernel then only updates its slice, pushes W / H and clears G (pre_reduced)
+    from theanompi_b200.ops import cuda_impl
+    ti = 4                                                       # the (4096, 1024) tensor
+    lo = arena.offsets[ti]
+    hi = arena.offsets[ti + 1] if ti + 1 < len(arena.offsets) else arena.numel
+    O_, I_, B_ = 4096, 1024, 128
+    for algo in ["twoshot"] + (["nvls"] if gc.has_multicast else []):
+        reset(21)
+        arena.G.zero_()
+        torch.cuda.synchronize(); dist.barrier()
+        torch.manual_seed(500 + rank)
+        dym = torch.randn(B_, O_, device=dev).to(torch.bfloat16)
+        xin = torch.randn(B_, I_, device=dev).to(torch.bfloat16)
+        dws = [torch.empty(O_, I_, device=dev) for _ in range(world)]
+        dist.all_gather(dws, dym.float().t() @ xin.float())
+        gs = torch.zeros_like(arena.G)
+        gs[lo:lo + O_ * I_] = torch.stack(dws).sum(0).reshape(-1)
+        w_ref, u_ref = arena.W.clone(), arena.U.clone()
+        ref.sgd_flat(w_ref, gs, u_ref, arena.lr_mult_vector(), arena.wd_vector(), 0.05, 0.9, False, 1.0 / world)
+        gc.configure_gemm_rs(arena, [(lo, hi)])
+        dw_view = arena.G[lo:lo + O_ * I_].view(O_, I_)
+        for rep in range(2):                                     # second round: G must have been cleared by the first
+            if rep:
+                arena.W.copy_(w0_rs); arena.U.zero_(); arena.refresh_shadow()
+                torch.cuda.synchronize(); dist.barrier()
+            else:
+                w0_rs = arena.W.clone()
+            cuda_impl.gemm(dym, xin, O_, I_, B_, a_mn=True, b_mn=True, out=dw_view, lda=O_, ldb=I_, ldc=I_)
+            gc.fused_allreduce_sgd(arena, lo, hi, 0.9, False, algo=algo, max_blocks=24, pre_reduced=True)
+            torch.cuda.synchronize(); dist.barrier()
+            ew = float((arena.W[lo:hi] - w_ref[lo:hi]).abs().max())
+            assert ew < 2e-4, ("gemm reduce-scatter", algo, rep, ew)
+            assert float(arena.G[lo:hi].abs().max()) == 0.0, "G not cleared by the pre_reduced exchange"
+            wl = [torch.empty_like(arena.W) for _ in range(world)]
+            dist.all_gather(wl, arena.W.clone())
+            assert all(torch.equal(wl[0][lo:hi], x[lo:hi]) for x in wl)
+        results["gemm_rs_" + algo] = dict(err_w=ew)
+        L.gemm_rs_clear()
+
     # plain allreduce G -> R (sum) and in-place weight averaging
     for algo in algos:
         reset(11)

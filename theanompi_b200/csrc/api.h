@@ -28,6 +28,8 @@ struct FusedArgs {
   float inv_k;
   long long lo, hi;                                  // element range, multiples of kArenaBlock
   int wire16;                                        // gradients travel as bf16 (cast into the wire region first)
+  int pre_reduced;                                   // the range's gradients were already reduce-scattered into their owner's G by the
+                                                     // wgrad GEMM epilogues (gemm_rs_*): skip the gather, zero G after use
 };
 
 struct ReduceArgs {
@@ -42,6 +44,12 @@ struct ReduceArgs {
 
 // ---- gemm_tcgen05.cu
 void gemm_set_debug(int flags);
+// Reduce-scatter fused into the wgrad GEMM epilogue: register the peer views of the gradient region and the tensors whose
+// fp32 GEMM output (C pointer inside [c_lo, c_hi)) must be red.add-ed into the OWNER rank's G instead of stored locally.
+// Ownership = the two-shot exchange kernel's partition of the bucket [blo, blo + world * per) in 1024-element blocks.
+void gemm_rs_configure(int world, const void* const* peer_g /*[world]*/, const void* local_g);
+void gemm_rs_add_range(const void* c_lo, const void* c_hi, long long blo, long long per);
+void gemm_rs_clear();
 int gemm_plan_splits(int tiles, int num_kb, int sms);          // split-K factor the launcher would pick
 int gemm_plan_tall(long long M, int nt, int out_bf16, int sms);   // 1 = 256-row CTA tiles   // bottleneck probe knobs of the tcgen05 GEMM (see Params::dbg)
 void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,

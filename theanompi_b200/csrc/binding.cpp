@@ -48,6 +48,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
 
   // ---------------------------------------------------------------- GEMM
   m.def("gemm_set_debug", &gemm_set_debug);
+  m.def("gemm_rs_add_range", [](ptr_t c_lo, ptr_t c_hi, long long blo, long long per) { gemm_rs_add_range(P(c_lo), P(c_hi), blo, per); });
+  m.def("gemm_rs_clear", &gemm_rs_clear);
   m.def("gemm_plan_splits", &gemm_plan_splits);
   m.def("gemm_plan_tall", &gemm_plan_tall);
   m.def("gemm_bf16", [](ptr_t A, ptr_t B, ptr_t C, ptr_t bias, int M, int N, int K, long long lda, long long ldb, long long ldc,
@@ -156,14 +158,24 @@ PYBIND11_MODULE(_tmpi_native, m) {
       .def("fused_allreduce_sgd",
            [](PyComm& c, long long w_off, long long g_off, long long u_off, long long h_off, long long wire_off, ptr_t block_group,
               std::vector<float> lr_mult, std::vector<float> wd, std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k,
-              long long lo, long long hi, int wire16, int algo, int max_blocks, ptr_t st) {
+              long long lo, long long hi, int wire16, int algo, int max_blocks, ptr_t st, int pre_reduced) {
              FusedArgs a;
+             a.pre_reduced = pre_reduced;
              a.ctx = c.pa->ctx();
              a.w_off = w_off; a.g_off = g_off; a.u_off = u_off; a.h_off = h_off; a.wire_off = wire_off;
              a.block_group = (const uint8_t*)P(block_group);
              a.tab = make_table(lr_mult, wd, exch);
              a.lr_ptr = (const float*)P(lr_ptr); a.mu = mu; a.nesterov = nesterov; a.inv_k = inv_k; a.lo = lo; a.hi = hi; a.wire16 = wire16;
              fused_allreduce_sgd(a, algo, max_blocks, S(st));
+           }, py::arg("w_off"), py::arg("g_off"), py::arg("u_off"), py::arg("h_off"), py::arg("wire_off"), py::arg("block_group"),
+           py::arg("lr_mult"), py::arg("wd"), py::arg("exch"), py::arg("lr_ptr"), py::arg("mu"), py::arg("nesterov"), py::arg("inv_k"),
+           py::arg("lo"), py::arg("hi"), py::arg("wire16"), py::arg("algo"), py::arg("max_blocks"), py::arg("st"), py::arg("pre_reduced") = 0)
+      .def("configure_gemm_rs", [](PyComm& c, long long g_off) {
+             // peer views of the gradient region for the reduce-scatter GEMM epilogue
+             const CommCtx x = c.pa->ctx();
+             const void* peers[kMaxRanks];
+             for (int p = 0; p < x.world; ++p) peers[p] = reinterpret_cast<const char*>(x.arena[p]) + g_off;
+             gemm_rs_configure(x.world, peers, peers[x.rank]);
            })
       .def("allreduce_flat",
            [](PyComm& c, long long src_off, long long dst_off, long long h_off, ptr_t block_group, std::vector<float> lr_mult,

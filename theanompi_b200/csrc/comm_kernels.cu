@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const Fused
   const long long nb = bhi - blo;
   const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
   const int R = a.ctx.rank, Wn = a.ctx.world;
-  if (a.wire16) {
+  if (a.wire16 && !a.pre_reduced) {
     // block b casts, for every owner r, the strip of r's slice that block b of rank r will read
     for (int r = 0; r < Wn; ++r) {
       const long long s0 = blo + r * per, s1 = min(bhi, s0 + per);
@@ -251,7 +251,14 @@ __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const Fused
       if (b < s1) { const int g = a.block_group[b]; if (a.tab.exch[g]) grp[u] = g; }
       if (grp[u] >= 0) {
         const long long i = b * kArenaBlock + threadIdx.x * 4;
-        if (use_nvls) {
+        if (a.pre_reduced) {
+          // the wgrad GEMM epilogues of every rank already red.add-ed their tiles into THIS rank's G (reduce-scatter fused into
+          // the producer): consume the sum and clear it for the next step (the closing barrier orders the clear before any
+          // peer's next add)
+          float* Gl = region<float>(a.ctx, R, a.g_off) + i;
+          gs[u] = *reinterpret_cast<const float4*>(Gl);
+          *reinterpret_cast<float4*>(Gl) = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else if (use_nvls) {
           gs[u] = a.wire16 ? unpack_bf16x4(mc_ld_reduce_bf16x4(reinterpret_cast<char*>(a.ctx.mc_arena) + a.wire_off + i * 2))
                            : mc_ld_reduce_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.g_off) + i);
         } else {
@@ -304,6 +311,7 @@ void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStrea
   if (nb <= 0) return;
   if (algo == 2 && a.ctx.mc_arena == nullptr) throw std::runtime_error("fused_allreduce_sgd: NVLS requested without a multicast mapping");
   const bool wide = a.ctx.world > 4;                     // keep (U x world) peer loads per thread around 8..16
+  if (a.pre_reduced && algo == 0) algo = a.ctx.mc_arena ? 2 : 1;     // ownership is the two-shot partition
   if (algo == 0) {
     if (wide) fused_oneshot_sgd_kernel<2><<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);
     else fused_oneshot_sgd_kernel<4><<<pick_grid(nb, max_blocks), kThreads, 0, st>>>(a);

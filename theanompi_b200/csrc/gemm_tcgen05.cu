@@ -17,7 +17,9 @@
 #include "common.cuh"
 #include "api.h"
 #include <cuda.h>
+#include <algorithm>
 #include <map>
+#include <vector>
 #include <mutex>
 #include <tuple>
 
@@ -80,7 +82,28 @@ struct Params {
   int groups;           // 1 or 2
   int group_m;          // tile raster: m-tiles per band (0 = plain m-fastest order); see tile_mn()
   int dbg;              // bottleneck probe (scripts/gemm_probe.py): 1 = skip A loads, 2 = skip B loads, 4 = skip the MMAs
+  // reduce-scatter fused into the epilogue (fp32 wgrad outputs living in the symmetric gradient arena): element e of the G
+  // region is owned by rank ((e >> 10) - rs_blo) / rs_per; every 16-byte vector is red.add-ed into the OWNER's G over NVLink
+  // (rs_g[q] = rank q's G region as mapped here) instead of being stored locally.  rs_world == 0: off.
+  int rs_world = 0, rs_rank = 0;
+  unsigned rs_blo = 0, rs_per = 1;
+  long long rs_e0 = 0;  // element index of C[0, 0] inside the G region
+  float* rs_g[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+// owner-rank address of element e of the gradient region (no dynamic indexing of the kernel-parameter array)
+__device__ __forceinline__ float* rs_addr(const Params& p, long long e, bool& local) {
+  unsigned owner = ((unsigned)(e >> 10) - p.rs_blo) / p.rs_per;
+  if (owner >= (unsigned)p.rs_world) owner = (unsigned)p.rs_world - 1u;
+  float* base = p.rs_g[0];
+#pragma unroll
+  for (int q = 1; q < kMaxRanks; ++q) if (owner == (unsigned)q) base = p.rs_g[q];
+  local = owner == (unsigned)p.rs_rank;
+  return base + e;
+}
+__device__ __forceinline__ void red_add_sys_f32(float* addr, float v) {
+  asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -564,7 +587,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               if (gm < p.M) {
                 const uint4 val = *reinterpret_cast<const uint4*>(wstage + (size_t)rr * pitch + (size_t)lv * 16);
                 uint8_t* gp = gbase + gm * p.ldc * esz;
-                if (p.atomic_out) {
+                if (p.rs_world > 0) {
+                  // fused reduce-scatter: this 16-byte vector of dW goes to the rank that owns it in the exchange
+                  bool local;
+                  float* d = rs_addr(p, p.rs_e0 + gm * p.ldc + nb + lv * 4, local);
+                  if (local) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(val.x)),
+                                 "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
+                  } else {
+                    red_add_sys_f32(d, __uint_as_float(val.x)); red_add_sys_f32(d + 1, __uint_as_float(val.y));
+                    red_add_sys_f32(d + 2, __uint_as_float(val.z)); red_add_sys_f32(d + 3, __uint_as_float(val.w));
+                  }
+                } else if (p.atomic_out) {
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(val.x)),
                                "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
                 } else {
@@ -577,7 +611,12 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           }
           if (!m_ok || nb >= n_end) continue;
           const bool full = (nb + 32 <= n_end);
-          if (p.atomic_out) {
+          if (p.rs_world > 0) {
+            const long long e0 = p.rs_e0 + (long long)m * p.ldc + nb;
+            for (int j = 0; j < 32; ++j) {
+              if (full || nb + j < n_end) { bool local; red_add_sys_f32(rs_addr(p, e0 + j, local), v[j]); }
+            }
+          } else if (p.atomic_out) {
             float* dst = reinterpret_cast<float*>(Cg_ptr) + (long long)m * p.ldc + nb;
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
@@ -708,6 +747,53 @@ static bool use_tall_tiles(long long M, int nt, int out_bf16, int sms) {
 
 void gemm_set_debug(int flags) { gemm::g_dbg = flags; }
 
+// ---- reduce-scatter epilogue registry (see api.h)
+namespace gemm {
+struct RsRange { const char* lo; const char* hi; long long blo, per; };
+static int g_rs_world = 0, g_rs_rank = 0;
+static float* g_rs_peer[kMaxRanks] = {};
+static const char* g_rs_local = nullptr;
+static std::vector<RsRange> g_rs_ranges;
+static std::mutex g_rs_mu;
+// fills the rs_* fields of p when C lies in a registered tensor; returns true if the epilogue will reduce-scatter
+static bool rs_lookup(const void* C, Params& p) {
+  std::lock_guard<std::mutex> lk(g_rs_mu);
+  if (g_rs_world < 2) return false;
+  const char* c = reinterpret_cast<const char*>(C);
+  for (const RsRange& r : g_rs_ranges) {
+    if (c >= r.lo && c < r.hi) {
+      p.rs_world = g_rs_world; p.rs_rank = g_rs_rank;
+      p.rs_blo = (unsigned)r.blo; p.rs_per = (unsigned)std::max<long long>(1, r.per);
+      p.rs_e0 = (long long)((c - g_rs_local) / 4);
+      for (int q = 0; q < kMaxRanks; ++q) p.rs_g[q] = q < g_rs_world ? g_rs_peer[q] : nullptr;
+      return true;
+    }
+  }
+  return false;
+}
+}  // namespace gemm
+
+void gemm_rs_configure(int world, const void* const* peer_g, const void* local_g) {
+  std::lock_guard<std::mutex> lk(gemm::g_rs_mu);
+  if (world > kMaxRanks) throw std::runtime_error("gemm_rs_configure: too many ranks");
+  gemm::g_rs_world = world;
+  gemm::g_rs_local = reinterpret_cast<const char*>(local_g);
+  gemm::g_rs_rank = 0;
+  for (int q = 0; q < world; ++q) {
+    gemm::g_rs_peer[q] = reinterpret_cast<float*>(const_cast<void*>(peer_g[q]));
+    if (peer_g[q] == local_g) gemm::g_rs_rank = q;
+  }
+  gemm::g_rs_ranges.clear();
+}
+void gemm_rs_add_range(const void* c_lo, const void* c_hi, long long blo, long long per) {
+  std::lock_guard<std::mutex> lk(gemm::g_rs_mu);
+  gemm::g_rs_ranges.push_back({reinterpret_cast<const char*>(c_lo), reinterpret_cast<const char*>(c_hi), blo, per});
+}
+void gemm_rs_clear() {
+  std::lock_guard<std::mutex> lk(gemm::g_rs_mu);
+  gemm::g_rs_world = 0; gemm::g_rs_ranges.clear();
+}
+
 // host-side planning helpers, exported so the wave arithmetic can be unit-tested without a GPU
 int gemm_plan_splits(int tiles, int num_kb, int sms) { return gemm::choose_splits(tiles, num_kb, sms); }
 int gemm_plan_tall(long long M, int nt, int out_bf16, int sms) { return gemm::use_tall_tiles(M, nt, out_bf16, sms) ? 1 : 0; }
@@ -752,7 +838,12 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   p.mt = tall ? (M + 2 * BM - 1) / (2 * BM) : mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
   p.group_m = (p.mt > 12 && nt > 12) ? (tall ? 8 : 12) : 0;
   p.cHo = p.cWo = p.cS = p.cP = p.cKH = p.cKW = p.cCg = p.c_chunks = 0;
-  if (splits > 1) {
+  // wgrad outputs registered for the fused reduce-scatter: every vector is red.add-ed into its owner's G (the exchange kernel
+  // clears G after consuming it, so there is no memset here — a memset would race with the peers' adds)
+  const bool rs = (!out_bf16) && bias_mode == 0 && !relu && alpha == 1.f && (ldc % 4) == 0 && rs_lookup(C, p);
+  if (rs) {
+    p.atomic_out = 1;
+  } else if (splits > 1) {
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
     check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");
   }

@@ -531,6 +531,7 @@ class FC(Layer):
             self.W = Normal((n_out, n_in), std=0.005)
             self.b = Constant((n_out,), val=0.1)
         _tag(self.W.val, "W", "W"); _tag(self.b.val, "b", "b")
+        self.W.val.rs_ok = True      # dW comes from ONE fp32 GEMM straight into gbuf: eligible for the fused reduce-scatter
         self.relu = relu
         self.params = [self.W.val, self.b.val]
         self.weight_type = ["W", "b"]
@@ -560,6 +561,7 @@ class Softmax(Layer):
             self.W = Normal((n_out, n_in))
             self.b = Constant((n_out,), val=0)
         _tag(self.W.val, "W", "W"); _tag(self.b.val, "b", "b")
+        self.W.val.rs_ok = True      # as FC: the logits' weight gradient is one fp32 GEMM into gbuf
         self.params = [self.W.val, self.b.val]
         self.weight_type = ["W", "b"]
         self.output_shape = tuple(self.input_shape[:-1]) + (n_out,)

@@ -200,9 +200,10 @@ class FlatArena(object):
         return self._ex_vec
 
     # ------------------------------------------------------------------ buckets (reverse layer order for overlap)
-    def make_buckets(self, bucket_bytes):
+    def make_buckets(self, bucket_bytes, solo=()):
         """Split the arena into contiguous block ranges.  Bucket 0 holds the LAST
-        parameters (their gradients are ready first in backward)."""
+        parameters (their gradients are ready first in backward).  Parameters listed in
+        ``solo`` always get a bucket of their own."""
         target = max(BLOCK, int(bucket_bytes) // 4)
         buckets = []
         hi = self.numel
@@ -210,7 +211,7 @@ class FlatArena(object):
         while i >= 0:
             lo = self.offsets[i]
             members = [i]
-            while i - 1 >= 0 and hi - self.offsets[i - 1] <= target:
+            while i not in solo and i - 1 >= 0 and (i - 1) not in solo and hi - self.offsets[i - 1] <= target:
                 i -= 1
                 lo = self.offsets[i]
                 members.append(i)

@@ -32,7 +32,11 @@ from ..utils import nvtx
 
 FUSED = {"fused": ("auto", False), "fused16": ("auto", True), "oneshot": ("oneshot", False),
          "oneshot16": ("oneshot", True), "twoshot": ("twoshot", False), "twoshot16": ("twoshot", True),
-         "nvls": ("nvls", False), "nvls16": ("nvls", True)}
+         "nvls": ("nvls", False), "nvls16": ("nvls", True),
+         # experimental (opt-in): reduce-scatter of the big FC gradients fused into the wgrad GEMM epilogue — each rank's
+         # tcgen05 GEMM red.adds its dW tiles straight into the owner rank's G over NVLink, the exchange kernel only updates
+         # its slice, all-gathers W / H and clears G
+         "fused_rs": ("auto", False)}
 
 
 # --------------------------------------------------------------------------- p2p helpers (ref :10-33)
@@ -118,10 +122,38 @@ class BSP_Exchanger(object):
         self.exch.prepare(ctx, src, dst)
 
     # ------------------------------------------------------------------ fused path
+    def _rs_params(self):
+        """Indices of the parameters whose gradient is produced by one fp32 GEMM straight into ``gbuf`` (native FC / Softmax
+        weights) and is big enough to be worth a bucket of its own."""
+        out = set()
+        for i, p in enumerate(self.arena.params):
+            if getattr(p, "rs_ok", False) and p.dim() == 2 and p.shape[0] % 8 == 0 and p.shape[1] % 8 == 0 and p.numel() >= (1 << 20):
+                out.add(i)
+        return out
+
     def _setup_buckets(self):
         a = self.arena
+        self.rs = self.exch_strategy == "fused_rs"
         bb = self.bucket_bytes or (a.numel * 4 if not self.overlap else 32 << 20)
-        self.buckets = a.make_buckets(bb) if self.overlap else [dict(lo=0, hi=a.numel, params=list(range(len(a.params))))]
+        if self.rs:
+            solo = self._rs_params()
+            self.buckets = a.make_buckets(bb if self.overlap else a.numel * 4, solo=solo)
+            ranges = []
+            for b in self.buckets:
+                b["rs"] = len(b["params"]) == 1 and b["params"][0] in solo
+                if b["rs"]:
+                    ranges.append((b["lo"], b["hi"]))
+            # G must be clear everywhere before the first producer adds into a peer, and stays clear afterwards (the exchange
+            # kernel zeroes what it consumed)
+            a.G.zero_()
+            torch.cuda.synchronize(a.device)
+            self.comm.Barrier()
+            self.gpucomm.configure_gemm_rs(a, ranges)
+            self.gpucomm.barrier()
+            torch.cuda.synchronize(a.device)
+            self.comm.Barrier()
+        else:
+            self.buckets = a.make_buckets(bb) if self.overlap else [dict(lo=0, hi=a.numel, params=list(range(len(a.params))))]
         self._pending = [0] * len(self.buckets)
         self._bucket_of = {}
         for bi, b in enumerate(self.buckets):
@@ -148,7 +180,7 @@ class BSP_Exchanger(object):
             big = int(os.environ.get("TMPI_OVERLAP_BLOCKS", "64"))     # measured at 2 ranks: 16 → 4.5 ms, 32 → 3.1, 64 → 2.17, 148 → 2.28
             blocks = big if (b["hi"] - b["lo"]) * 4 > (8 << 20) else min(8, big)
         self.gpucomm.fused_allreduce_sgd(self.arena, b["lo"], b["hi"], mu, m.use_nesterov_momentum,
-                                         algo=self.algo, wire16=self.wire16, max_blocks=blocks)
+                                         algo=self.algo, wire16=self.wire16, max_blocks=blocks, pre_reduced=b.get("rs", False))
 
     def _on_ready(self, p):
         """Called by a backward kernel wrapper right after it enqueued the gradient of ``p``."""
@@ -175,7 +207,8 @@ class BSP_Exchanger(object):
             cur.wait_stream(self.side)
             self._reset_pending()
         else:
-            self._launch_bucket(0)
+            for bi in range(len(self.buckets)):                   # one bucket, or solo reduce-scatter buckets + the rest
+                self._launch_bucket(bi)
 
     # ------------------------------------------------------------------ the per-iteration call
     def exchange(self, recorder):

@@ -173,16 +173,33 @@ class SymmetricComm(object):
             return ALGO["oneshot"]
         return ALGO["nvls"] if self.has_multicast else ALGO["twoshot"]
 
-    def fused_allreduce_sgd(self, arena, lo, hi, mu, nesterov, inv_k=None, algo="auto", wire16=False, max_blocks=None):
+    def fused_allreduce_sgd(self, arena, lo, hi, mu, nesterov, inv_k=None, algo="auto", wire16=False, max_blocks=None,
+                            pre_reduced=False):
+        """``pre_reduced``: the range's gradients were already reduce-scattered into their owner's G by the wgrad GEMM
+        epilogues (``configure_gemm_rs`` / ``gemm_rs_add_range``) — the kernel skips the gather, updates its slice, pushes
+        W / H and clears G."""
         from ..ops.cuda_impl import _table
         lrm, wd, ex = _table(arena)
         h_off = arena.layout["H"] if arena.H is not None else -1
         a = self.pick_algo((hi - lo) * (2 if wire16 else 4), algo)
+        if pre_reduced and a == ALGO["oneshot"]:
+            a = ALGO["nvls"] if self.has_multicast else ALGO["twoshot"]
         self.pa.fused_allreduce_sgd(arena.layout["W"], arena.layout["G"], arena.layout["U"], h_off, arena.layout["R"],
                                     arena.block_group.data_ptr(), lrm, wd, ex, arena.hyper.data_ptr(), float(mu),
                                     int(bool(nesterov)), float(inv_k if inv_k is not None else 1.0 / self.size),
-                                    int(lo), int(hi), int(bool(wire16)), a, self._blocks(max_blocks), self._stream())
+                                    int(lo), int(hi), int(bool(wire16)), a, self._blocks(max_blocks), self._stream(),
+                                    int(bool(pre_reduced)))
         return a
+
+    def configure_gemm_rs(self, arena, ranges):
+        """Arm the reduce-scatter epilogue of the GEMM for the given single-tensor buckets ``[(lo, hi), …]`` (element ranges
+        of the arena): fp32 GEMM outputs written into those parts of ``arena.G`` are red.add-ed into the owner rank's G."""
+        self.pa.configure_gemm_rs(int(arena.layout["G"]))
+        g0 = arena.G.data_ptr()
+        for lo, hi in ranges:
+            nb = (hi - lo) // self.L.ARENA_BLOCK
+            per = (nb + self.size - 1) // self.size
+            self.L.gemm_rs_add_range(g0 + lo * 4, g0 + hi * 4, lo // self.L.ARENA_BLOCK, per)
 
     def allreduce(self, arena, src, dst, scale, lo=0, hi=None, algo="auto", refresh_shadow=False, skip_local=True,
                   max_blocks=None):

@@ -346,3 +346,20 @@ def test_conv_pool_block_single_node_equals_composition_cpu(groups):
 
     for a, b in zip(run(True), run(False)):
         assert torch.allclose(a, b, atol=1e-5), float((a - b).abs().max())
+
+
+def test_arena_buckets_with_solo_parameters():
+    """``make_buckets(solo=…)`` (used by the reduce-scatter strategy): a solo parameter is a bucket of its own, buckets stay
+    contiguous, cover the arena exactly once and are ordered last-parameter-first."""
+    from theanompi_b200.parallel.arena import FlatArena
+    shapes = [(16, 3, 3, 8), (16,), (2048, 1024), (2048,), (1000, 2048), (1000,)]
+    params = [torch.randn(s) * 0.1 for s in shapes]
+    arena = FlatArena(params, ["W" if len(s) > 1 else "b" for s in shapes], torch.device("cpu"), weight_decay=0.0)
+    plain = arena.make_buckets(1 << 30)
+    assert len(plain) == 1 and plain[0]["lo"] == 0 and plain[0]["hi"] == arena.numel
+    bs = arena.make_buckets(1 << 30, solo={2, 4})
+    assert [b["params"] for b in bs] == [[5], [4], [3], [2], [0, 1]]
+    assert bs[0]["hi"] == arena.numel and bs[-1]["lo"] == 0
+    for a, b in zip(bs, bs[1:]):
+        assert a["lo"] == b["hi"]
+    assert all(b["lo"] % 1024 == 0 and b["hi"] % 1024 == 0 for b in bs)

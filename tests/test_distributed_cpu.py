@@ -115,6 +115,13 @@ def test_rule_easgd_cpu(tmp_path, monkeypatch):
     assert _run_rule(tm.EASGD, ["cpu0", "cpu1", "cpu2"], extra_env={"TMPI_EASGD_TAU": "2"}) == 0
 
 
+def test_rule_asgd_cpu(tmp_path, monkeypatch):
+    """ASGD (delta-push exchanger behind the EASGD runtime) incl. validation / stop, which both copy the center to the worker."""
+    import theanompi_b200 as tm
+    monkeypatch.chdir(tmp_path)
+    assert _run_rule(tm.ASGD, ["cpu0", "cpu1", "cpu2"], extra_env={"TMPI_EASGD_TAU": "2"}) == 0
+
+
 def test_rule_gosgd_cpu(tmp_path, monkeypatch):
     import theanompi_b200 as tm
     monkeypatch.chdir(tmp_path)

@@ -15,6 +15,7 @@ struct CommCtx {
   uint32_t* epoch;                       // local: per-block barrier epoch counters [kMaxCommBlocks]
   void* mc_arena;                        // multicast mapping of the arena (NVLS) or nullptr
   int rank, world;
+  long long spin_limit;                  // clock64 cycles a flag barrier may spin before it traps (TMPI_BARRIER_TIMEOUT_S)
 };
 
 struct FusedArgs {
@@ -90,7 +91,7 @@ void col2im(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off
             long long ldcol, cudaStream_t st);
 void pad_rows(const void* src, void* dst, long long rows, int cols, long long src_ld, long long dst_ld, cudaStream_t st);
 void transpose_bf16(const void* src, void* dst, int R, int C, cudaStream_t st);
-void crop_mirror_norm(const void* x, int in_kind, const void* mean, int mean_mode, float scale, void* out, int out_bf16, const void* offs,
+void crop_mirror_norm(const void* x, int in_kind, const void* mean, int mean_mode, float scale, const void* cscale, void* out, int out_bf16, const void* offs,
                       const void* flips, int N, int H, int W, int C, int ch, int cw, int Cout, cudaStream_t st);
 
 // ---- comm_kernels.cu
@@ -99,8 +100,15 @@ void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group,
 void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStream_t st);
 void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t st);
 void device_barrier(const CommCtx& c, cudaStream_t st);
-void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, cudaStream_t st);
-void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, cudaStream_t st);
+void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, int lockfree, cudaStream_t st);
+// device-side ticket lock in rank `owner`'s signal pad (EASGD: the center); local_state = >= 1 uint32 of local device memory
+void ticket_acquire(const CommCtx& c, int owner, void* local_state, cudaStream_t st);
+void ticket_release(const CommCtx& c, int owner, void* local_state, cudaStream_t st);
+void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, const void* gate, cudaStream_t st);
+// device-side gossip (GOSGD): state = 64 uint32 of local device memory, [0] holds the push-sum weight (float)
+void gosgd_push(const CommCtx& c, void* state, int dest, long long w_off, long long snap_off, long long n, int max_blocks, cudaStream_t st);
+void gosgd_poll_merge(const CommCtx& c, void* state, long long w_off, long long h_off, long long snap_off, long long n, int max_blocks,
+                      cudaStream_t st);
 void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, long long n, int max_blocks, cudaStream_t st);
 void bias_act_cast(const void* acc, const void* bias, void* y, int R, int C, int relu, cudaStream_t st);
 void cast_flat(const void* src, void* dst, long long n, int kind, cudaStream_t st);

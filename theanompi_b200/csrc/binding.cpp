@@ -111,19 +111,20 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.def("pad_rows", [](ptr_t src, ptr_t dst, long long rows, int cols, long long src_ld, long long dst_ld, ptr_t st) {
     pad_rows(P(src), P(dst), rows, cols, src_ld, dst_ld, S(st)); });
   m.def("transpose_bf16", [](ptr_t src, ptr_t dst, int R, int C, ptr_t st) { transpose_bf16(P(src), P(dst), R, C, S(st)); });
-  m.def("crop_mirror_norm", [](ptr_t x, int in_kind, ptr_t mean, int mean_mode, float scale, ptr_t out, int out_bf16, ptr_t offs, ptr_t flips,
-                               int N, int H, int W, int C, int ch, int cw, int Cout, ptr_t st) {
-    crop_mirror_norm(P(x), in_kind, P(mean), mean_mode, scale, P(out), out_bf16, P(offs), P(flips), N, H, W, C, ch, cw, Cout, S(st)); });
+  m.def("crop_mirror_norm", [](ptr_t x, int in_kind, ptr_t mean, int mean_mode, float scale, ptr_t cscale, ptr_t out, int out_bf16, ptr_t offs,
+                               ptr_t flips, int N, int H, int W, int C, int ch, int cw, int Cout, ptr_t st) {
+    crop_mirror_norm(P(x), in_kind, P(mean), mean_mode, scale, P(cscale), P(out), out_bf16, P(offs), P(flips), N, H, W, C, ch, cw, Cout, S(st)); });
 
   // ---------------------------------------------------------------- optimizer / legacy kernels
   m.def("sgd_flat", [](ptr_t W, ptr_t G, ptr_t U, ptr_t H, ptr_t block_group, std::vector<float> lr_mult, std::vector<float> wd,
                        std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k, long long lo, long long hi, int filter,
                        ptr_t st) {
     sgd_flat(P(W), P(G), P(U), P(H), P(block_group), make_table(lr_mult, wd, exch), P(lr_ptr), mu, nesterov, inv_k, lo, hi, filter, S(st)); });
-  m.def("easgd_elastic", [](ptr_t w, ptr_t h, ptr_t center, float alpha, long long n, int max_blocks, ptr_t st) {
-    easgd_elastic(P(w), P(h), P(center), alpha, n, max_blocks, S(st)); });
+  m.def("easgd_elastic", [](ptr_t w, ptr_t h, ptr_t center, float alpha, long long n, int max_blocks, ptr_t st, int lockfree) {
+    easgd_elastic(P(w), P(h), P(center), alpha, n, max_blocks, lockfree, S(st)); },
+    py::arg("w"), py::arg("h"), py::arg("center"), py::arg("alpha"), py::arg("n"), py::arg("max_blocks"), py::arg("st"), py::arg("lockfree") = 0);
   m.def("copy_flat", [](ptr_t dst, ptr_t dst_h, ptr_t src, long long n, int max_blocks, ptr_t st) {
-    copy_flat(P(dst), P(dst_h), P(src), n, max_blocks, S(st)); });
+    copy_flat(P(dst), P(dst_h), P(src), n, max_blocks, nullptr, S(st)); });
   m.def("gosgd_merge", [](ptr_t w, ptr_t h, ptr_t b, float a_self, float a_src, long long n, int max_blocks, ptr_t st) {
     gosgd_merge(P(w), P(h), P(b), a_self, a_src, n, max_blocks, S(st)); });
   m.def("bias_act_cast", [](ptr_t acc, ptr_t bias, ptr_t y, int R, int C, int relu, ptr_t st) { bias_act_cast(P(acc), P(bias), P(y), R, C, relu, S(st)); });
@@ -155,6 +156,13 @@ PYBIND11_MODULE(_tmpi_native, m) {
       .def("mode", [](PyComm& c) { return c.pa->mode(); })
       .def("vmm_error", [](PyComm& c) { return c.pa->vmm_error(); })
       .def("device_barrier", [](PyComm& c, ptr_t st) { device_barrier(c.pa->ctx(), S(st)); })
+      .def("ticket_acquire", [](PyComm& c, int owner, ptr_t local_state, ptr_t st) { ticket_acquire(c.pa->ctx(), owner, P(local_state), S(st)); })
+      .def("ticket_release", [](PyComm& c, int owner, ptr_t local_state, ptr_t st) { ticket_release(c.pa->ctx(), owner, P(local_state), S(st)); })
+      .def("gosgd_push", [](PyComm& c, ptr_t state, int dest, long long w_off, long long snap_off, long long n, int max_blocks, ptr_t st) {
+             gosgd_push(c.pa->ctx(), P(state), dest, w_off, snap_off, n, max_blocks, S(st)); })
+      .def("gosgd_poll_merge", [](PyComm& c, ptr_t state, long long w_off, long long h_off, long long snap_off, long long n, int max_blocks,
+                                  ptr_t st) { gosgd_poll_merge(c.pa->ctx(), P(state), w_off, h_off, snap_off, n, max_blocks, S(st)); })
+      .def("proto_words_offset", [](PyComm&) { return (long long)((size_t)kMaxCommBlocks * kMaxRanks + kMaxCommBlocks) * 4; })
       .def("fused_allreduce_sgd",
            [](PyComm& c, long long w_off, long long g_off, long long u_off, long long h_off, long long wire_off, ptr_t block_group,
               std::vector<float> lr_mult, std::vector<float> wd, std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k,

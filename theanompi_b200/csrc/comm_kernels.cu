@@ -89,7 +89,7 @@ __device__ __forceinline__ void block_barrier(const CommCtx& c) {
     while (true) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int)(v - target) >= 0) break;
-      if (clock64() - t0 > 60000000000LL) { __trap(); }
+      if (clock64() - t0 > c.spin_limit) { __trap(); }
     }
   }
   __syncthreads();
@@ -399,69 +399,289 @@ void device_barrier(const CommCtx& c, cudaStream_t st) {
   count_launch(); TMPI_CHECK_LAUNCH("device_barrier"); ::tmpi::check_capture(st, "device_barrier");
 }
 
+// ============================================================================ device-side protocol words
+// The 4 KiB tail of every rank's signal pad (peer-mapped like the rest of it) holds the words of the asynchronous rules:
+//   [0] EASGD next ticket   [1] EASGD now serving   [2] EASGD exchanges served
+//   [32 + 2*src], [33 + 2*src]   GOSGD inbox slot of sender `src`: {sequence number, push-sum weight bits}
+//   [96 + dst]                   GOSGD acknowledgements: receiver `dst` writes the sequence number it merged (on the SENDER's pad)
+__device__ __forceinline__ uint32_t* proto_words(const CommCtx& c, int p) {
+  return c.sig[p] + (size_t)kMaxCommBlocks * kMaxRanks + kMaxCommBlocks;
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_sys_v4(float* p, float4 v) {
+  asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 // ============================================================================ EASGD elastic exchange (worker side, center over NVLink)
+// Reference: the server serialises workers with a blocking MPI recv and both sides broadcast their full model
+// (easgd_server.py:152-164, lib/exchanger.py:214-261).  Here the workers queue on the DEVICE: a ticket lock in the center
+// rank's signal pad (atom.acq_rel.sys take, st.release.sys hand-over) brackets ONE kernel on the worker's GPU that reads the
+// center over NVLink, computes d = α(w − c) and updates both sides.  Three stream-ordered launches (acquire → elastic →
+// release) instead of a grid-wide sync inside one kernel: no co-residency requirement, graph-capturable, and the host never
+// waits.  lockfree = 1: no lock at all — the center update is a vector red.add (commutative, so no update can be lost) and
+// the workers run fully concurrently.
+__global__ void ticket_acquire_kernel(CommCtx c, int owner, uint32_t* local) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t* lock = proto_words(c, owner);
+  uint32_t my;
+  asm volatile("atom.acq_rel.sys.global.add.u32 %0, [%1], 1;" : "=r"(my) : "l"(lock) : "memory");
+  local[0] = my;
+  const long long t0 = clock64();
+  while (ld_acquire_sys_u32(lock + 1) != my) {
+    if (clock64() - t0 > c.spin_limit) __trap();
+    __nanosleep(200);
+  }
+}
+__global__ void ticket_release_kernel(CommCtx c, int owner, uint32_t* local) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t* lock = proto_words(c, owner);
+  __threadfence_system();
+  asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(lock + 2) : "memory");
+  st_release_sys_u32(lock + 1, local[0] + 1u);
+}
+
+// U arena blocks in flight per CTA iteration: U independent 16 B NVLink loads per thread cover the ~2 us round trip
+template <int U>
 __global__ void __launch_bounds__(kThreads) easgd_elastic_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ h, float* c /*peer*/,
-                                                                 float alpha, long long nblk) {
-  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-    const long long i = b * kArenaBlock + threadIdx.x * 4;
-    float4 wv = *reinterpret_cast<const float4*>(w + i);
-    float4 cv = ld_sys_f4(c + i);
-    const float4 d = make_float4(alpha * (wv.x - cv.x), alpha * (wv.y - cv.y), alpha * (wv.z - cv.z), alpha * (wv.w - cv.w));
-    wv.x -= d.x; wv.y -= d.y; wv.z -= d.z; wv.w -= d.w;
-    cv.x += d.x; cv.y += d.y; cv.z += d.z; cv.w += d.w;
-    *reinterpret_cast<float4*>(w + i) = wv;
-    st_f4(c + i, cv);
-    if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(wv);
+                                                                 float alpha, long long nblk, int lockfree) {
+  for (long long b0 = blockIdx.x; b0 < nblk; b0 += (long long)gridDim.x * U) {
+    float4 cv[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      if (b < nblk) {
+        const long long i = b * kArenaBlock + threadIdx.x * 4;
+        cv[u] = ld_sys_f4(c + i);
+        wv[u] = *reinterpret_cast<const float4*>(w + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      if (b >= nblk) continue;
+      const long long i = b * kArenaBlock + threadIdx.x * 4;
+      const float4 d = make_float4(alpha * (wv[u].x - cv[u].x), alpha * (wv[u].y - cv[u].y), alpha * (wv[u].z - cv[u].z),
+                                   alpha * (wv[u].w - cv[u].w));
+      wv[u].x -= d.x; wv[u].y -= d.y; wv[u].z -= d.z; wv[u].w -= d.w;
+      *reinterpret_cast<float4*>(w + i) = wv[u];
+      if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(wv[u]);
+      if (lockfree) red_add_sys_v4(c + i, d);
+      else st_f4(c + i, add4(cv[u], d));
+    }
   }
   __threadfence_system();
 }
-void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, cudaStream_t st) {
+
+void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, int lockfree, cudaStream_t st) {
   if (n % kArenaBlock) throw std::runtime_error("easgd_elastic: n must be block aligned");
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
-  easgd_elastic_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (float*)center, alpha, nb);
+  easgd_elastic_kernel<4><<<pick_grid((nb + 3) / 4, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (float*)center, alpha, nb,
+                                                                                lockfree);
   count_launch(); TMPI_CHECK_LAUNCH("easgd_elastic"); ::tmpi::check_capture(st, "easgd_elastic");
 }
+void ticket_acquire(const CommCtx& c, int owner, void* local_state, cudaStream_t st) {
+  ticket_acquire_kernel<<<1, 32, 0, st>>>(c, owner, (uint32_t*)local_state);
+  count_launch(); TMPI_CHECK_LAUNCH("ticket_acquire"); ::tmpi::check_capture(st, "ticket_acquire");
+}
+void ticket_release(const CommCtx& c, int owner, void* local_state, cudaStream_t st) {
+  ticket_release_kernel<<<1, 32, 0, st>>>(c, owner, (uint32_t*)local_state);
+  count_launch(); TMPI_CHECK_LAUNCH("ticket_release"); ::tmpi::check_capture(st, "ticket_release");
+}
 
-// dst = src (+ bf16 shadow) over peer memory: EASGD copy_to_local, GOSGD push into the peer's mailbox region
-__global__ void __launch_bounds__(kThreads) copy_flat_kernel(float* dst, __nv_bfloat16* dst_h, const float* src, long long nblk) {
-  for (long long b = blockIdx.x; b < nblk; b += gridDim.x) {
-    const long long i = b * kArenaBlock + threadIdx.x * 4;
-    const float4 v = ld_sys_f4(src + i);
-    st_f4(dst + i, v);
-    if (dst_h) *reinterpret_cast<uint2*>(dst_h + i) = pack_bf16x4(v);
+// dst = src (+ bf16 shadow) over peer memory: EASGD copy_to_local, GOSGD snapshot.  `gate` (optional, device word): the copy
+// runs only when *gate != 0 (GOSGD: the push was admitted by gosgd_push_begin).
+template <int U>
+__global__ void __launch_bounds__(kThreads) copy_flat_kernel(float* dst, __nv_bfloat16* dst_h, const float* src, long long nblk,
+                                                             const uint32_t* __restrict__ gate) {
+  if (gate && *gate == 0u) return;
+  for (long long b0 = blockIdx.x; b0 < nblk; b0 += (long long)gridDim.x * U) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      if (b < nblk) v[u] = ld_sys_f4(src + b * kArenaBlock + threadIdx.x * 4);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long b = b0 + (long long)u * gridDim.x;
+      if (b >= nblk) continue;
+      const long long i = b * kArenaBlock + threadIdx.x * 4;
+      st_f4(dst + i, v[u]);
+      if (dst_h) *reinterpret_cast<uint2*>(dst_h + i) = pack_bf16x4(v[u]);
+    }
   }
   __threadfence_system();
 }
-void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, cudaStream_t st) {
+void copy_flat(void* dst, void* dst_h, const void* src, long long n, int max_blocks, const void* gate, cudaStream_t st) {
   if (n % kArenaBlock) throw std::runtime_error("copy_flat: n must be block aligned");
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
-  copy_flat_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)dst, (__nv_bfloat16*)dst_h, (const float*)src, nb);
+  copy_flat_kernel<4><<<pick_grid((nb + 3) / 4, max_blocks), kThreads, 0, st>>>((float*)dst, (__nv_bfloat16*)dst_h, (const float*)src, nb,
+                                                                            (const uint32_t*)gate);
   count_launch(); TMPI_CHECK_LAUNCH("copy_flat"); ::tmpi::check_capture(st, "copy_flat");
 }
 
-// ============================================================================ GOSGD merge:  w ← (a_self·w + a_src·b) / (a_self + a_src)
-// `b` may be a local mailbox region or the sender's weights mapped over NVLink (pull-merge, one pass).
+// ============================================================================ GOSGD:  w ← (a_self·w + a_src·b) / (a_self + a_src)
+// Host-driven form (CPU-mirrored semantics, tests): coefficients passed by value, `b` = local mailbox or a peer's snapshot.
+template <int U>
 __global__ void __launch_bounds__(kThreads) gosgd_merge_kernel(float* __restrict__ w, __nv_bfloat16* __restrict__ h, const float* b,
-                                                               float a_self, float a_src, long long nblk) {
-  const float inv = 1.f / (a_self + a_src);
-  const float ca = a_self * inv, cb = a_src * inv;
-  for (long long blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-    const long long i = blk * kArenaBlock + threadIdx.x * 4;
-    float4 wv = *reinterpret_cast<const float4*>(w + i);
-    const float4 bv = ld_sys_f4(b + i);
-    wv.x = ca * wv.x + cb * bv.x; wv.y = ca * wv.y + cb * bv.y; wv.z = ca * wv.z + cb * bv.z; wv.w = ca * wv.w + cb * bv.w;
-    *reinterpret_cast<float4*>(w + i) = wv;
-    if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(wv);
+                                                               float ca, float cb, long long nblk) {
+  for (long long b0 = blockIdx.x; b0 < nblk; b0 += (long long)gridDim.x * U) {
+    float4 bv[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long blk = b0 + (long long)u * gridDim.x;
+      if (blk < nblk) {
+        const long long i = blk * kArenaBlock + threadIdx.x * 4;
+        bv[u] = ld_sys_f4(b + i);
+        wv[u] = *reinterpret_cast<const float4*>(w + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long blk = b0 + (long long)u * gridDim.x;
+      if (blk >= nblk) continue;
+      const long long i = blk * kArenaBlock + threadIdx.x * 4;
+      float4 o;
+      o.x = ca * wv[u].x + cb * bv[u].x; o.y = ca * wv[u].y + cb * bv[u].y; o.z = ca * wv[u].z + cb * bv[u].z; o.w = ca * wv[u].w + cb * bv[u].w;
+      *reinterpret_cast<float4*>(w + i) = o;
+      if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(o);
+    }
   }
 }
 void gosgd_merge(void* w, void* h, const void* b, float a_self, float a_src, long long n, int max_blocks, cudaStream_t st) {
   if (n % kArenaBlock) throw std::runtime_error("gosgd_merge: n must be block aligned");
   const long long nb = n / kArenaBlock;
   if (nb <= 0) return;
-  gosgd_merge_kernel<<<pick_grid(nb, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (const float*)b, a_self, a_src, nb);
+  const float inv = 1.f / (a_self + a_src);
+  gosgd_merge_kernel<4><<<pick_grid((nb + 3) / 4, max_blocks), kThreads, 0, st>>>((float*)w, (__nv_bfloat16*)h, (const float*)b, a_self * inv,
+                                                                              a_src * inv, nb);
   count_launch(); TMPI_CHECK_LAUNCH("gosgd_merge"); ::tmpi::check_capture(st, "gosgd_merge");
+}
+
+// ---- device-side gossip protocol (no host message, no stream synchronisation on the path; ref lib/exchanger.py:484-584
+//      blocks the sender inside ncclBcast until the receiver joins).
+// Local state words (uint32 / float bits, one small device buffer per rank):
+//   [0] alpha (float)  [1] push admitted flag  [2] last dest (+1; 0 = none)  [3] sequence of the outstanding push
+//   [4] pushes done    [5] pushes skipped (previous snapshot still being pulled)  [6] merges done
+//   [8] merge: chosen src (+1; 0 = none)  [9] merge: src's sequence  [10] ca (float)  [11] cb (float)
+//   [16 + src] last sequence merged from src        [32 + dst] sequence counter of pushes sent to dst
+__global__ void gosgd_push_begin_kernel(CommCtx c, uint32_t* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  uint32_t ok = 1u;
+  const uint32_t last = st[2];
+  if (last != 0u) {
+    // my snapshot region is single-buffered: the previous receiver must have pulled it (it acknowledges on MY pad)
+    const uint32_t acked = ld_acquire_sys_u32(proto_words(c, c.rank) + 96 + (last - 1u));
+    if (acked != st[3]) ok = 0u;
+  }
+  st[1] = ok;
+  if (ok) {
+    float a = __uint_as_float(st[0]) * 0.5f;                    // push-sum: keep half, ship half
+    st[0] = __float_as_uint(a);
+  } else {
+    st[5] += 1u;
+  }
+}
+__global__ void gosgd_push_end_kernel(CommCtx c, uint32_t* st, int dest) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (st[1] == 0u) return;
+  __threadfence_system();                                       // the snapshot (copy_flat before me on this stream) is visible
+  const uint32_t seq = st[32 + dest] + 1u;
+  st[32 + dest] = seq; st[2] = (uint32_t)dest + 1u; st[3] = seq; st[4] += 1u;
+  uint32_t* inbox = proto_words(c, dest) + 32 + 2 * c.rank;
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(inbox + 1), "r"(st[0]) : "memory");     // shipped weight = what I kept
+  st_release_sys_u32(inbox, seq);
+}
+// receiver: pick at most one pending push (lowest rank first, fair enough for p << 1)
+__global__ void gosgd_poll_kernel(CommCtx c, uint32_t* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st[8] = 0u;
+  const uint32_t* inbox = proto_words(c, c.rank) + 32;
+  for (int s = 0; s < c.world; ++s) {
+    if (s == c.rank) continue;
+    const uint32_t seq = ld_acquire_sys_u32(inbox + 2 * s);
+    if (seq != st[16 + s]) {
+      const float a_src = __uint_as_float(ld_acquire_sys_u32(inbox + 2 * s + 1));
+      const float a_self = __uint_as_float(st[0]);
+      const float inv = 1.f / (a_self + a_src);
+      st[8] = (uint32_t)s + 1u; st[9] = seq;
+      st[10] = __float_as_uint(a_self * inv); st[11] = __float_as_uint(a_src * inv);
+      st[0] = __float_as_uint(a_self + a_src);
+      return;
+    }
+  }
+}
+template <int U>
+__global__ void __launch_bounds__(kThreads) gosgd_pull_merge_kernel(CommCtx c, const uint32_t* __restrict__ st, long long w_off, long long h_off,
+                                                                    long long snap_off, long long nblk) {
+  const uint32_t chosen = st[8];
+  if (chosen == 0u) return;
+  const int src = (int)chosen - 1;
+  const float ca = __uint_as_float(st[10]), cb = __uint_as_float(st[11]);
+  float* w = region<float>(c, c.rank, w_off);
+  __nv_bfloat16* h = h_off >= 0 ? region<__nv_bfloat16>(c, c.rank, h_off) : nullptr;
+  const float* b = region<float>(c, src, snap_off);
+  for (long long b0 = blockIdx.x; b0 < nblk; b0 += (long long)gridDim.x * U) {
+    float4 bv[U], wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long blk = b0 + (long long)u * gridDim.x;
+      if (blk < nblk) {
+        const long long i = blk * kArenaBlock + threadIdx.x * 4;
+        bv[u] = ld_sys_f4(b + i);
+        wv[u] = *reinterpret_cast<const float4*>(w + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long blk = b0 + (long long)u * gridDim.x;
+      if (blk >= nblk) continue;
+      const long long i = blk * kArenaBlock + threadIdx.x * 4;
+      float4 o;
+      o.x = ca * wv[u].x + cb * bv[u].x; o.y = ca * wv[u].y + cb * bv[u].y; o.z = ca * wv[u].z + cb * bv[u].z; o.w = ca * wv[u].w + cb * bv[u].w;
+      *reinterpret_cast<float4*>(w + i) = o;
+      if (h) *reinterpret_cast<uint2*>(h + i) = pack_bf16x4(o);
+    }
+  }
+}
+__global__ void gosgd_ack_kernel(CommCtx c, uint32_t* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const uint32_t chosen = st[8];
+  if (chosen == 0u) return;
+  const int src = (int)chosen - 1;
+  st[16 + src] = st[9]; st[6] += 1u; st[8] = 0u;
+  __threadfence_system();
+  st_release_sys_u32(proto_words(c, src) + 96 + c.rank, st[9]);       // the sender may overwrite its snapshot now
+}
+
+void gosgd_push(const CommCtx& c, void* state, int dest, long long w_off, long long snap_off, long long n, int max_blocks, cudaStream_t st) {
+  if (n % kArenaBlock) throw std::runtime_error("gosgd_push: n must be block aligned");
+  if (dest < 0 || dest >= c.world || dest == c.rank) throw std::runtime_error("gosgd_push: bad destination");
+  uint32_t* s = (uint32_t*)state;
+  gosgd_push_begin_kernel<<<1, 32, 0, st>>>(c, s);
+  char* base = reinterpret_cast<char*>(c.arena[c.rank]);
+  const long long nb = n / kArenaBlock;
+  copy_flat_kernel<4><<<pick_grid((nb + 3) / 4, max_blocks), kThreads, 0, st>>>((float*)(base + snap_off), nullptr, (const float*)(base + w_off), nb,
+                                                                            s + 1);
+  gosgd_push_end_kernel<<<1, 32, 0, st>>>(c, s, dest);
+  count_launch(3); TMPI_CHECK_LAUNCH("gosgd_push"); ::tmpi::check_capture(st, "gosgd_push");
+}
+void gosgd_poll_merge(const CommCtx& c, void* state, long long w_off, long long h_off, long long snap_off, long long n, int max_blocks,
+                      cudaStream_t st) {
+  if (n % kArenaBlock) throw std::runtime_error("gosgd_poll_merge: n must be block aligned");
+  uint32_t* s = (uint32_t*)state;
+  const long long nb = n / kArenaBlock;
+  gosgd_poll_kernel<<<1, 32, 0, st>>>(c, s);
+  gosgd_pull_merge_kernel<4><<<pick_grid((nb + 3) / 4, max_blocks), kThreads, 0, st>>>(c, s, w_off, h_off, snap_off, nb);
+  gosgd_ack_kernel<<<1, 32, 0, st>>>(c, s);
+  count_launch(3); TMPI_CHECK_LAUNCH("gosgd_poll_merge"); ::tmpi::check_capture(st, "gosgd_poll_merge");
 }
 
 // ============================================================================ reference kernels K1..K5 (legacy strategies)

@@ -595,8 +595,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(val.x)),
                                  "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
                   } else {
-                    red_add_sys_f32(d, __uint_as_float(val.x)); red_add_sys_f32(d + 1, __uint_as_float(val.y));
-                    red_add_sys_f32(d + 2, __uint_as_float(val.z)); red_add_sys_f32(d + 3, __uint_as_float(val.w));
+                    // ONE 16-byte vector reduction per NVLink packet (the first version issued four scalar 4-byte atomics per
+                    // vector and was 60 % slower than the separate exchange kernel)
+                    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(__uint_as_float(val.x)),
+                                 "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w)) : "memory");
                   }
                 } else if (p.atomic_out) {
                   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gp), "f"(__uint_as_float(val.x)),

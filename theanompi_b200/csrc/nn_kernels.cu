@@ -984,8 +984,8 @@ void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S,
 // per-thread divisions (the one-thread-per-pixel version with 64-bit div/mod was issue-bound: 230 instructions per pixel).
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(128) crop_mirror_norm_kernel(const Tin* __restrict__ x, const float* __restrict__ mean, int mean_mode,
-                                        float scale, Tout* __restrict__ out, const int* __restrict__ offs, const uint8_t* __restrict__ flips,
-                                        int N, int H, int W, int C, int ch, int cw, int Cout) {
+                                        float scale, const float* __restrict__ cscale, Tout* __restrict__ out, const int* __restrict__ offs,
+                                        const uint8_t* __restrict__ flips, int N, int H, int W, int C, int ch, int cw, int Cout) {
   const int ox = blockIdx.y * blockDim.x + threadIdx.x;
   if (ox >= cw) return;
   const int oy = blockIdx.x % ch, n = blockIdx.x / ch;
@@ -997,7 +997,9 @@ __global__ void __launch_bounds__(128) crop_mirror_norm_kernel(const Tin* __rest
   Tout* o = out + ((long long)blockIdx.x * cw + ox) * Cout;
   if (C == 3 && Cout == 3) {
     const float m0 = mean_mode == 0 ? mp[0] : mp[0], m1 = mean_mode == 0 ? mp[0] : mp[1], m2 = mean_mode == 0 ? mp[0] : mp[2];
-    const float v0 = ((float)src[0] - m0) * scale, v1 = ((float)src[1] - m1) * scale, v2 = ((float)src[2] - m2) * scale;
+    // per-channel 1/std on top of the scalar scale (ref proc_load_mpi.py:99: (arr - img_mean) / 255. / img_std)
+    const float s0 = cscale ? scale * cscale[0] : scale, s1 = cscale ? scale * cscale[1] : scale, s2 = cscale ? scale * cscale[2] : scale;
+    const float v0 = ((float)src[0] - m0) * s0, v1 = ((float)src[1] - m1) * s1, v2 = ((float)src[2] - m2) * s2;
     o[0] = (Tout)v0; o[1] = (Tout)v1; o[2] = (Tout)v2;
     return;
   }
@@ -1005,18 +1007,18 @@ __global__ void __launch_bounds__(128) crop_mirror_norm_kernel(const Tin* __rest
     float v = 0.f;
     if (c < C) {
       const float m = mean_mode == 0 ? mp[0] : mp[c];
-      v = ((float)src[c] - m) * scale;
+      v = ((float)src[c] - m) * (cscale ? scale * cscale[c] : scale);
     }
     o[c] = (Tout)v;
   }
 }
 
-void crop_mirror_norm(const void* x, int in_kind /*0 u8, 1 bf16, 2 f32*/, const void* mean, int mean_mode, float scale, void* out,
+void crop_mirror_norm(const void* x, int in_kind /*0 u8, 1 bf16, 2 f32*/, const void* mean, int mean_mode, float scale, const void* cscale, void* out,
                       int out_bf16, const void* offs, const void* flips, int N, int H, int W, int C, int ch, int cw, int Cout, cudaStream_t st) {
   if ((long long)H * W * C >= (1LL << 31) || (long long)N * ch >= (1LL << 31)) throw std::runtime_error("crop_mirror_norm: image too large");
   const dim3 g((unsigned)(N * ch), (unsigned)((cw + 127) / 128));
   auto M = (const float*)mean; auto O = (const int*)offs; auto F = (const uint8_t*)flips;
-#define CMN(TI, TO) crop_mirror_norm_kernel<TI, TO><<<g, 128, 0, st>>>((const TI*)x, M, mean_mode, scale, (TO*)out, O, F, N, H, W, C, ch, cw, Cout)
+#define CMN(TI, TO) crop_mirror_norm_kernel<TI, TO><<<g, 128, 0, st>>>((const TI*)x, M, mean_mode, scale, (const float*)cscale, (TO*)out, O, F, N, H, W, C, ch, cw, Cout)
   if (in_kind == 0) { if (out_bf16) CMN(uint8_t, __nv_bfloat16); else CMN(uint8_t, float); }
   else if (in_kind == 1) { if (out_bf16) CMN(__nv_bfloat16, __nv_bfloat16); else CMN(__nv_bfloat16, float); }
   else { if (out_bf16) CMN(float, __nv_bfloat16); else CMN(float, float); }

@@ -309,6 +309,15 @@ CommCtx PeerArena::ctx() const {
   c.epoch = reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(sig_[rank_]) + (size_t)kMaxCommBlocks * kMaxRanks * 4);
   c.mc_arena = mc_;
   c.rank = rank_; c.world = world_;
+  // a rank stuck behind a slow disk / loader / debugger must not kill the job: the device-side flag barriers spin for
+  // TMPI_BARRIER_TIMEOUT_S seconds (default 600; at ~2 GHz) before they trap
+  static const long long limit = [] {
+    const char* e = getenv("TMPI_BARRIER_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (!(s > 0)) s = 600.0;
+    return (long long)(s * 2.0e9);
+  }();
+  c.spin_limit = limit;
   return c;
 }
 

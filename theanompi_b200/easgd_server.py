@@ -10,9 +10,12 @@ tag=199)`` → ``process_request`` → ``send(reply, tag=200)`` → ``action_aft
 ``stop`` (``:132-143``).  A worker joining marks every worker ``adj_lr`` (``:60-65``).
 
 B200-native data plane: the center lives in the server's symmetric arena; a worker's
-``exchange`` is ONE kernel on the worker that reads/updates the center over NVLink —
-the server only serialises access (it waits for the worker's completion message), so the
-center GPU does no work at all.  On CPU (gloo) both sides swap flat copies.
+``exchange`` is ONE kernel on the worker that reads/updates the center over NVLink,
+bracketed by a device-side ticket lock that lives in this rank's signal pad
+(``csrc/comm_kernels.cu``: ``ticket_acquire`` / ``ticket_release``).  Workers queue on the
+device; the server process is not on the data path at all (no request, no reply, no host
+synchronisation per exchange) and the center GPU does no work.  On CPU (gloo) both sides
+swap flat copies through the request / reply protocol.
 
 Reference bugs fixed: the server no longer exits on the first ``stop`` while other
 workers still wait for replies; training data IS sharded across workers.
@@ -114,11 +117,10 @@ class EASGD_Server(MPI_GPU_Process):
         if message == "sync_register":
             self.worker_gpucomm[str(worker_id)] = self.get_intranode_pair_comm(pair=(0, worker_rank))
         elif message in ("exchange", "copy_to_local"):
+            # CPU / gloo data plane only: on GPUs the workers never send these — they queue on the device-side ticket lock in
+            # this rank's signal pad and run the elastic kernel against the center over NVLink without involving the server
             self.exchanger.peer = worker_rank
-            if self.exchanger.use_p2p:
-                # the worker's kernel works on the center over NVLink; hold the "lock" until it is done
-                self.comm.recv(source=worker_rank, tag=TAG_DONE)
-            elif message == "exchange":
+            if message == "exchange":
                 self.exchanger.exchange()
             else:
                 self.exchanger.copy_to_local()

@@ -8,8 +8,8 @@ the center; ``adjust_hyperp``; ``val`` → copy center to local, full validation
 recorder + snapshot every 2 uepochs, copy to local again; ``stop``.
 
 The exchange is one fused kernel on this worker's GPU operating on the center's memory
-over NVLink (``csrc/comm_kernels.cu: easgd_elastic_kernel``); the server only grants the
-turn.  Unlike the reference (``:273-276``) every worker trains on its own shard.
+over NVLink (``csrc/comm_kernels.cu: easgd_elastic_kernel``), queued behind a device-side
+ticket lock — enqueued on the training stream, the host never waits for it.  Unlike the reference (``:273-276``) every worker trains on its own shard.
 """
 from __future__ import annotations
 
@@ -49,11 +49,14 @@ class EASGD_Worker(MPI_GPU_Process):
         return self.comm.recv(source=self.server_rank, tag=TAG_REP)
 
     def comm_action(self, message, action=None, action_args=None):
+        if getattr(self, "exchanger", None) is not None and getattr(self.exchanger, "use_p2p", False):
+            # GPU data plane: the turn is taken on the device (ticket lock in the center's signal pad) — no message
+            if action:
+                action(*action_args) if action_args else action()
+            return None
         reply = self.comm_request(message)
         if action:
             action(*action_args) if action_args else action()
-        if getattr(self, "exchanger", None) is not None and getattr(self.exchanger, "use_p2p", False):
-            self.comm.send("done", dest=self.server_rank, tag=TAG_DONE)      # release the center
         return reply
 
     def register_worker(self):
@@ -78,7 +81,6 @@ class EASGD_Worker(MPI_GPU_Process):
         if os.environ.get("TMPI_EASGD_EXCHANGER") == "asgd":
             self.exchanger = ASGD_Exchanger(model.params, "worker", comm=self.comm, arena=model.arena)
             self.exchanger.use_p2p = False
-            self.exchanger.copy_to_local = lambda: None
         else:
             self.exchanger = EASGD_Exchanger(alpha=float(os.environ.get("TMPI_EASGD_ALPHA", worker_alpha)),
                                              param_list=model.params, etype="worker", comm=self.comm,
@@ -92,6 +94,18 @@ class EASGD_Worker(MPI_GPU_Process):
         recorder.print_val_info(batch_i)
         model.current_info = recorder.get_latest_val_info()
         recorder.save(batch_i, model.shared_lr.get_value())
+
+    def train_round(self, model, exchange_freq, batch_i):
+        """τ local iterations, progress report, elastic exchange (ref ``easgd_worker.py:150-175``)."""
+        recorder = self.recorder
+        for i in range(exchange_freq):
+            for subb_i in range(model.n_subb):
+                model.train_iter(batch_i, recorder)
+            batch_i += 1
+            recorder.print_train_info(batch_i)
+        self.comm_request(dict(done=exchange_freq))
+        self.exchange()
+        return batch_i
 
     def run(self, model, exchange_freq=None, snapshot_freq=2, snapshot_path="./snapshots/"):
         from .utils.helper_funcs import save_model
@@ -110,13 +124,7 @@ class EASGD_Worker(MPI_GPU_Process):
                 if lastmode == "val":
                     model.reset_iter("train")
                 lastmode = "train"
-                for i in range(exchange_freq):
-                    for subb_i in range(model.n_subb):
-                        model.train_iter(batch_i, recorder)
-                    batch_i += 1
-                    recorder.print_train_info(batch_i)
-                self.comm_request(dict(done=exchange_freq))
-                self.exchange()
+                batch_i = self.train_round(model, exchange_freq, batch_i)
             elif mode == "adjust_hyperp":
                 uepoch, n_workers = self.comm_request("uepoch")
                 model.epoch = uepoch
@@ -136,6 +144,9 @@ class EASGD_Worker(MPI_GPU_Process):
                     recorder.end_epoch(batch_i, uepoch)
                     epoch_start = False
             elif mode == "stop":
+                if self.kind == "cuda":
+                    import torch
+                    torch.cuda.synchronize()                       # my last exchange has left the center
                 if self.verbose:                                  # final test of the center by the recording worker
                     self.copy_to_local()
                     if lastmode == "train":

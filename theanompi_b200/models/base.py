@@ -182,15 +182,25 @@ class ModelBase(object):
                     out = self._step_body()
                 cur.wait_stream(self._gstream)
                 return out
+            ok, why = True, ""
             try:
                 self._capture()
             except Exception as e:  # noqa: BLE001
                 if not self._graph_auto:
                     raise
-                print("[%s] CUDA-graph capture of the training step failed (%s: %s) — running eager"
-                      % (getattr(self, "name", type(self).__name__), type(e).__name__, str(e)[:200]))
+                ok, why = False, "%s: %s" % (type(e).__name__, str(e)[:200])
+            ex = self.exchanger
+            if ex is not None and getattr(ex, "fused", False) and getattr(ex, "size", 1) > 1:
+                # the fused exchange pairs device-side barriers by launch order: either every rank replays the graph or
+                # every rank runs eager — agree on it (a capture that failed on one rank only would desynchronise them)
+                ok = all(ex.comm.allgather(bool(ok)))
+            if not ok:
+                print("[%s] CUDA-graph capture of the training step failed (%s) — running eager"
+                      % (getattr(self, "name", type(self).__name__), why or "on another rank"))
                 self.use_graph = False
                 self._graph = None
+                if ex is not None and hasattr(ex, "_reset_pending") and getattr(ex, "fused", False):
+                    ex._reset_pending()          # a half-captured step consumed some grad-ready callbacks
                 torch.cuda.synchronize()
                 return self._step_body()
         self._graph.replay()

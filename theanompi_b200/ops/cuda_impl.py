@@ -514,7 +514,13 @@ def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype
     assert out.dtype in (BF16, torch.float32)
     offsets = offsets.to(torch.int32).contiguous()
     flips = flips.to(torch.uint8).contiguous()
-    L().crop_mirror_norm(x.data_ptr(), kind, mean.data_ptr(), mode, float(std_scale), out.data_ptr(), int(out.dtype == BF16),
+    if isinstance(std_scale, torch.Tensor):                   # per-channel scale (1 / 255 / img_std)
+        cs = std_scale.to(device=x.device, dtype=torch.float32).contiguous()
+        assert cs.numel() == C
+        sc, cs_ptr = 1.0, cs.data_ptr()
+    else:
+        sc, cs_ptr = float(std_scale), 0
+    L().crop_mirror_norm(x.data_ptr(), kind, mean.data_ptr(), mode, sc, cs_ptr, out.data_ptr(), int(out.dtype == BF16),
                          offsets.data_ptr(), flips.data_ptr(), N, H, W, C, ch, cw, Cout, _st(x))
     return out
 

@@ -187,6 +187,8 @@ def crop_mirror_normalize(x_u8, mean, std_scale, crop_hw, offsets, flips, out_dt
     """
     N, H, W, C = x_u8.shape
     ch, cw = crop_hw
+    if isinstance(std_scale, torch.Tensor):
+        std_scale = std_scale.to(device=x_u8.device, dtype=torch.float32)
     x = (x_u8.float() - mean.float()) * std_scale
     out = torch.empty((N, ch, cw, C), dtype=torch.float32, device=x.device)
     for i in range(N):

@@ -249,6 +249,11 @@ class EASGD_Exchanger(object):
         self.peer = None                       # server: rank of the worker being served
         self.device = arena.W.device if arena is not None else param_list[0].device
         self.use_p2p = gpucomm is not None and self.device.type == "cuda"
+        # TMPI_EASGD_LOCKFREE=1: no ticket lock — the center is updated with vector red.add over NVLink (commutative: no
+        # update can be lost) and all workers exchange concurrently
+        self.lockfree = os.environ.get("TMPI_EASGD_LOCKFREE", "0") == "1"
+        self.max_blocks = int(os.environ.get("TMPI_EASGD_BLOCKS", "0")) or None
+        self.n_exchanges = 0
         if not self.use_p2p:
             n = arena.numel if arena is not None else sum(p.numel() for p in param_list)
             self.mirror = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -269,15 +274,33 @@ class EASGD_Exchanger(object):
             for p in self.param_list:
                 p.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
 
+    # ---- GPU data plane: everything below is enqueued on the worker's stream and returns immediately
+    def _lock_state(self):
+        if getattr(self, "_lstate", None) is None:
+            self._lstate = torch.zeros(4, dtype=torch.int32, device=self.device)
+        return self._lstate
+
+    def _p2p_section(self, body):
+        """Run ``body`` (kernel launches touching the center) under the device-side ticket lock of the center rank."""
+        gc = self.gpucomm
+        if self.lockfree:
+            body()
+            return
+        st = self._lock_state()
+        gc.ticket_acquire(self.server_rank, st)
+        body()
+        gc.ticket_release(self.server_rank, st)
+
     def exchange(self):
         if self.use_p2p:
             if self.etype == "worker":
                 from ..ops import native
                 a, gc = self.arena, self.gpucomm
                 center = gc.peer_region(self.server_rank, a.layout["W"], a.numel)
-                native.require().easgd_elastic(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(),
-                                               float(self.alpha), a.numel, gc._blocks(None), gc._stream())
-                torch.cuda.current_stream(self.device).synchronize()
+                self._p2p_section(lambda: native.require().easgd_elastic(
+                    a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(), float(self.alpha), a.numel,
+                    gc._blocks(self.max_blocks), gc._stream(), int(self.lockfree)))
+                self.n_exchanges += 1
             return
         other = self.peer if self.etype == "server" else self.server_rank
         mine = self._flat().contiguous()
@@ -298,9 +321,9 @@ class EASGD_Exchanger(object):
                 from ..ops import native
                 a, gc = self.arena, self.gpucomm
                 center = gc.peer_region(self.server_rank, a.layout["W"], a.numel)
-                native.require().copy_flat(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(),
-                                           a.numel, gc._blocks(None), gc._stream())
-                torch.cuda.current_stream(self.device).synchronize()
+                self._p2p_section(lambda: native.require().copy_flat(
+                    a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, center.data_ptr(), a.numel,
+                    gc._blocks(self.max_blocks), gc._stream()))
             return
         if self.etype == "server":
             dist.send(self._flat().contiguous(), self.peer, group=self.group)
@@ -339,27 +362,71 @@ class ASGD_Exchanger(object):
             self._unflat(self.buf.clone())
             self.last = self._flat().clone()
 
+    def copy_to_local(self):
+        """Worker ← center (before / after validation and at stop): the server sends its flat weights, the worker adopts
+        them and restarts its delta from there."""
+        if self.etype == "server":
+            dist.send(self._flat().contiguous(), self.peer, group=self.group)
+        else:
+            dist.recv(self.buf, self.server_rank, group=self.group)
+            self._unflat(self.buf.clone())
+            self.last = self._flat().clone()
+
 
 # =========================================================================== GOSGD
 class GOSGD_Exchanger(object):
+    """Gossip push-sum exchange (ref ``lib/exchanger.py:412-617``).
+
+    GPU data plane = a device-side protocol (``csrc/comm_kernels.cu``, ``gosgd_*``): the sender snapshots W into its R
+    region, halves its push-sum weight (a device scalar) and posts ``{seq, α}`` into the receiver's inbox slot in the
+    receiver's signal pad; every iteration the receiver runs ``poll → pull-merge → ack`` (three launches, no-ops when nothing
+    is pending) that blends the sender's snapshot over NVLink and acknowledges on the sender's pad.  No host message, no
+    ``stream.synchronize()`` — a push that finds the previous snapshot still un-pulled is skipped (counted) instead of
+    blocking, so two ranks pushing to each other cannot deadlock.  CPU / gloo: host mailbox + isend of the snapshot."""
     TAG_REQ, TAG_ACK = 700, 703
 
     def __init__(self, comm, gpucomm, model, p=0.01, seed=None, group=None):
         self.comm, self.gpucomm, self.model, self.p = comm, gpucomm, model, p
         self.rank, self.size = comm.rank, comm.size
         self.arena = model.arena
-        self.alpha = 1.0 / self.size                              # push-sum weight (ref :430)
+        self._alpha = 1.0 / self.size                             # push-sum weight (ref :430)
         self.rs = np.random.RandomState(seed if seed is not None else (1000 + 7919 * self.rank))
         self.group = group
         self.device = self.arena.W.device
         self.use_p2p = gpucomm is not None and self.device.type == "cuda"
         self._unacked = 0
         self._pending_sends = []
+        self.max_blocks = int(os.environ.get("TMPI_GOSGD_BLOCKS", "0")) or None
         if not self.use_p2p:
             self.b = torch.zeros(self.arena.numel, dtype=torch.float32, device=self.device)
             self.snap = torch.zeros_like(self.b)
+        else:
+            if "R" not in self.arena.layout:
+                _ = self.arena.R
+            self.state = torch.zeros(64, dtype=torch.int32, device=self.device)
+            self.state[:1].view(torch.float32).fill_(self._alpha)
+            self._count_tick = 0
         self.n_merged = 0
         self.n_pushed = 0
+
+    # ---- push-sum weight (device scalar on the GPU path)
+    @property
+    def alpha(self):
+        if self.use_p2p:
+            return float(self.state[:1].view(torch.float32).item())
+        return self._alpha
+
+    @alpha.setter
+    def alpha(self, v):
+        if self.use_p2p:
+            self.state[:1].view(torch.float32).fill_(float(v))
+        else:
+            self._alpha = float(v)
+
+    def device_counters(self):
+        """(pushes done, pushes skipped, merges done) as counted by the device protocol (synchronises)."""
+        st = self.state.cpu()
+        return int(st[4]), int(st[5]), int(st[6])
 
     # ---- Bernoulli draw + uniform peer (ref :586-617)
     def draw(self):
@@ -371,11 +438,37 @@ class GOSGD_Exchanger(object):
         d = self.rs.randint(0, self.size - 1)
         return d if d < self.rank else d + 1
 
+    def _share_counts(self, count_arr):
+        """Progress counters used for the epoch arithmetic travel through the store (best effort, every 16 calls): the device
+        protocol carries weights only.  Element-wise max, as for the host messages (SURVEY §2.9 #14)."""
+        if count_arr is None:
+            return
+        self._count_tick += 1
+        if self._count_tick % 16:
+            return
+        st, pre = self.comm.store, self.comm.prefix
+        st.set("%s/gosgd_count/%d" % (pre, self.rank), str(float(count_arr[self.rank])))
+        for r in range(self.size):
+            if r == self.rank:
+                continue
+            key = "%s/gosgd_count/%d" % (pre, r)
+            try:
+                if st.check([key]):
+                    count_arr[r] = max(count_arr[r], float(st.get(key)))
+            except Exception:  # noqa: BLE001
+                pass
+
     # ---- receiver side
     def process_messages(self, count_arr=None):
         """Drain inbound pushes: pull the sender's snapshot, blend, add its weight
         (ref ``:484-535``).  ``count_arr`` is merged element-wise (max) instead of being
         overwritten by the sender's view (SURVEY §2.9 #14)."""
+        if self.use_p2p:
+            a, gc = self.arena, self.gpucomm
+            gc.pa.gosgd_poll_merge(self.state.data_ptr(), int(a.layout["W"]), int(a.layout["H"]) if a.H is not None else -1,
+                                   int(a.layout["R"]), int(a.numel), gc._blocks(self.max_blocks), gc._stream())
+            self._share_counts(count_arr)
+            return 0
         while self.comm.iprobe(tag=self.TAG_ACK):
             self.comm.recv(tag=self.TAG_ACK)
             self._unacked -= 1
@@ -386,7 +479,7 @@ class GOSGD_Exchanger(object):
             if count_arr is not None and msg.get("count") is not None:
                 np.maximum(count_arr, np.asarray(msg["count"]), out=count_arr)
             self._merge_params_from(src, a_src)
-            self.alpha += a_src
+            self._alpha += a_src
             self.comm.send(self.rank, src, tag=self.TAG_ACK)
             merged += 1
         self.n_merged += merged
@@ -394,49 +487,50 @@ class GOSGD_Exchanger(object):
 
     def _merge_params_from(self, src, a_src):
         a = self.arena
-        if self.use_p2p:
-            from ..ops import native
-            gc = self.gpucomm
-            b = gc.peer_region(src, a.layout["R"], a.numel)       # sender's snapshot over NVLink
-            native.require().gosgd_merge(a.W.data_ptr(), a.H.data_ptr() if a.H is not None else 0, b.data_ptr(),
-                                         float(self.alpha), float(a_src), a.numel, gc._blocks(None), gc._stream())
-            torch.cuda.current_stream(self.device).synchronize()
-        else:
-            dist.recv(self.b, src, group=self.group)
-            from ..ops import reference as ref
-            with torch.no_grad():
-                ref.gosgd_merge(a.W, self.b, self.alpha, a_src)
-            a.refresh_shadow()
+        dist.recv(self.b, src, group=self.group)
+        from ..ops import reference as ref
+        with torch.no_grad():
+            ref.gosgd_merge(a.W, self.b, self._alpha, a_src)
+        a.refresh_shadow()
 
     # ---- sender side
     def push_message(self, dest, count_arr=None):
         """Snapshot my weights, halve my push-sum weight, notify ``dest`` and keep training
         (ref ``:538-584`` blocks inside ncclBcast until the receiver joins)."""
-        while self._unacked > 0:                                   # my snapshot buffer is still being pulled
-            self.process_messages(count_arr)
         a = self.arena
         if self.use_p2p:
-            from ..ops import native
             gc = self.gpucomm
-            native.require().copy_flat(a.R.data_ptr(), 0, a.W.data_ptr(), a.numel, gc._blocks(None), gc._stream())
-            torch.cuda.current_stream(self.device).synchronize()
-        else:
-            self.snap.copy_(a.W)
-        self.alpha *= 0.5
-        self.comm.send({"src": self.rank, "alpha": self.alpha,
+            gc.pa.gosgd_push(self.state.data_ptr(), int(dest), int(a.layout["W"]), int(a.layout["R"]), int(a.numel),
+                             gc._blocks(self.max_blocks), gc._stream())
+            self.n_pushed += 1
+            return
+        while self._unacked > 0:                                   # my snapshot buffer is still being pulled
+            self.process_messages(count_arr)
+        self.snap.copy_(a.W)
+        self._alpha *= 0.5
+        self.comm.send({"src": self.rank, "alpha": self._alpha,
                         "count": None if count_arr is None else np.asarray(count_arr).tolist()}, dest, tag=self.TAG_REQ)
         self._unacked += 1
-        if not self.use_p2p:
-            self._pending_sends = [w for w in self._pending_sends if not w.is_completed()]
-            self._pending_sends.append(dist.isend(self.snap, dest, group=self.group))
+        self._pending_sends = [w for w in self._pending_sends if not w.is_completed()]
+        self._pending_sends.append(dist.isend(self.snap, dest, group=self.group))
         self.n_pushed += 1
+
+    def _outstanding(self):
+        """GPU path: is my last snapshot still waiting to be pulled?  (synchronises)"""
+        st = self.state.cpu()
+        last = int(st[2])
+        if last == 0:
+            return False
+        acked = int(self.gpucomm.proto_words(self.gpucomm.rank)[96 + last - 1].item())
+        return (acked & 0xFFFFFFFF) != (int(st[3]) & 0xFFFFFFFF)
 
     def finish(self, count_arr=None):
         """Clean shutdown without deadlock: (1) keep serving inbound pushes until all of mine
         are acknowledged, (2) announce completion, (3) keep serving until every rank has
         announced — at that point no push can be in flight any more."""
         import time
-        while self._unacked > 0:
+        busy = self._outstanding if self.use_p2p else (lambda: self._unacked > 0)
+        while busy():
             self.process_messages(count_arr)
             time.sleep(0.0005)
         key = "%s/gosgd_done" % self.comm.prefix
@@ -445,5 +539,10 @@ class GOSGD_Exchanger(object):
             self.process_messages(count_arr)
             time.sleep(0.0005)
         self.process_messages(count_arr)
+        if self.use_p2p:
+            self.process_messages(count_arr)
+            torch.cuda.synchronize(self.device)
+            pushed, skipped, merged = self.device_counters()
+            self.n_pushed, self.n_skipped, self.n_merged = pushed, skipped, merged
         for w in self._pending_sends:
             w.wait()

@@ -141,6 +141,22 @@ class SymmetricComm(object):
         nb = numel * torch.empty((), dtype=dtype).element_size()
         return self.peer_bytes(p)[byte_off:byte_off + nb].view(dtype)
 
+    def proto_words(self, p):
+        """int32 view of rank ``p``'s protocol words (tail of its signal pad): EASGD ticket lock, GOSGD inbox / acks —
+        layout in ``csrc/comm_kernels.cu``."""
+        key = ("proto", p)
+        if key not in self._tensors:
+            off = int(self.pa.proto_words_offset())
+            self._tensors[key] = tensor_from_ptr(self.pa.sig_ptr(p) + off, 4096, self.device, self.pa).view(torch.int32)
+        return self._tensors[key]
+
+    # ------------------------------------------------------------------ device-side ticket lock (EASGD center)
+    def ticket_acquire(self, owner, state):
+        self.pa.ticket_acquire(int(owner), state.data_ptr(), self._stream())
+
+    def ticket_release(self, owner, state):
+        self.pa.ticket_release(int(owner), state.data_ptr(), self._stream())
+
     # ------------------------------------------------------------------ kernels
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream

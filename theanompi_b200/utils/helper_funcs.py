@@ -125,7 +125,7 @@ def check_model_cdd(model):
 
 
 # --------------------------------------------------------------------------- snapshots
-def save_model(model, path, verbose):
+def save_model(model, path, verbose, recorder=None):
     """Reference-compatible snapshot (ref ``:230-260``) + a full resumable checkpoint."""
     os.makedirs(path, exist_ok=True)
     if hasattr(model, "save") and callable(model.save):
@@ -139,7 +139,7 @@ def save_model(model, path, verbose):
                 pickle.dump([p.detach().cpu() for p in model.params], f, protocol=pickle.HIGHEST_PROTOCOL)
         lr = model.shared_lr.get_value() if hasattr(model, "shared_lr") else 0.0
         np.save(os.path.join(path, "lr_%d.npy" % model.epoch), np.float32(lr))
-    save_checkpoint(model, os.path.join(path, "ckpt_%d.pt" % model.epoch))
+    save_checkpoint(model, os.path.join(path, "ckpt_%d.pt" % model.epoch), recorder=recorder)
     if verbose:
         print("\nweights saved at epoch %d" % model.epoch)
     try:

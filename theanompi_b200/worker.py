@@ -104,6 +104,7 @@ class BSP_Worker(MPI_GPU_Process):
             model.epoch = epoch
             recorder.start_epoch()
             self.lr_warmup(model, epoch)
+            self.comm.Barrier()
             exch_iteration = 0
             batch_i = 0
             n_train = model.data.n_batch_train if max_batches is None else min(max_batches, model.data.n_batch_train)
@@ -139,9 +140,14 @@ class BSP_Worker(MPI_GPU_Process):
             model.current_info = recorder.get_latest_val_info()
             if self.rank == 0:
                 recorder.save(batch_i * self.size, model.shared_lr.get_value() if hasattr(model, "shared_lr") else 0)
-            if epoch % snapshot_freq == 0 and self.rank == 0:
-                save_model(model, snapshot_path, verbose=self.verbose)
+            # lr schedule BEFORE the snapshot: ckpt_<epoch> must carry the lr epoch+1 will train with (every lr_step of the
+            # zoo is a multiple of snapshot_freq — saving first would lose that decay on resume)
             model.adjust_hyperp(epoch)
+            if epoch % snapshot_freq == 0 and self.rank == 0:
+                save_model(model, snapshot_path, verbose=self.verbose, recorder=recorder)
+            # rank 0 may have spent seconds writing files: park everybody on the HOST here — the next fused step spins in a
+            # device-side flag barrier, which is the wrong place to wait for a slow disk
+            self.comm.Barrier()
             if hasattr(model, "print_info"):
                 model.print_info(recorder, verbose=self.verbose)
             recorder.end_epoch(batch_i * self.size, epoch)

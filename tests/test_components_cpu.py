@@ -286,8 +286,9 @@ def test_loader_handoff_identity_cpu():
     raw = np.empty((4, 32, 32, 3), np.uint8)
     src = d.read(d.train_img[0], raw)
     raw = src.numpy() if src is not None else raw
-    want = ((raw.astype(np.float32) - 127.5) / 255.0)[:, 4:28, 4:28, :]
-    assert np.allclose(b0.x.numpy(), want, atol=1e-6)
+    std = np.array([0.229, 0.224, 0.225], np.float32)          # (x - mean) / 255 / img_std  (ref proc_load_mpi.py:99)
+    want = ((raw.astype(np.float32) - 127.5) / 255.0 / std)[:, 4:28, 4:28, :]
+    assert np.allclose(b0.x.numpy(), want, atol=1e-5)
     b1 = ld.get()
     assert b1.item == d.train_img[1]
     ld.drain(); d.para_load_close()

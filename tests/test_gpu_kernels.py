@@ -295,6 +295,11 @@ def test_crop_mirror_normalize():
     flips = torch.tensor([0, 1, 1, 0], dtype=torch.uint8, device=DEV)
     out = ops.crop_mirror_normalize(x, mean, 1 / 255.0, (27, 27), offs, flips)
     want = ref.crop_mirror_normalize(x.cpu(), mean.cpu(), 1 / 255.0, (27, 27), offs.cpu(), flips.cpu())
+    # per-channel scale (1 / 255 / img_std, ref proc_load_mpi.py:99)
+    cs = torch.tensor([1 / 255.0 / 0.229, 1 / 255.0 / 0.224, 1 / 255.0 / 0.225])
+    out_c = ops.crop_mirror_normalize(x, mean, cs.to(DEV), (27, 27), offs, flips)
+    want_c = ref.crop_mirror_normalize(x.cpu(), mean.cpu(), cs, (27, 27), offs.cpu(), flips.cpu())
+    assert torch.allclose(out_c.float().cpu(), want_c.float(), atol=3e-2, rtol=2e-2)
     assert rel_err(out.cpu(), want) < 1e-2
 
 

@@ -6,7 +6,8 @@ Same API: ``batch_data`` (``:109-148``), ``extend_data`` (``:150-164``),
 ``para_load_init`` / ``para_load_close`` (``:226-321``).
 
 Storage: one ``.npy`` file per 128-image batch, uint8 NHWC ``[128,256,256,3]``
-(the reference used hickle ``.hkl`` in c01b float; hickle is optional here).  When
+(the reference used hickle ``.hkl`` in c01b layout; ``.hkl`` files are read too when the ``hickle`` package is
+importable — it is not part of this image — and transposed to NHWC).  When
 the directory does not exist the dataset is **synthetic**: file names are
 ``synthetic://<split>/<index>`` and ``read`` fills the pinned buffer from a small
 pool of pre-generated random batches (there is no network / dataset in the build
@@ -63,8 +64,10 @@ class ImageNet_data(object):
             val_labels = rs.randint(0, self.n_class, nva * file_batch_size).astype(np.int64)
             img_mean = np.full((self.height, self.width, self.channels), 127.5, dtype=np.float32)
         else:
-            train_filenames = sorted(glob.glob(self.data_path + train_folder + "/*.npy"))
-            val_filenames = sorted(glob.glob(self.data_path + val_folder + "/*.npy"))
+            train_filenames = sorted(glob.glob(self.data_path + train_folder + "/*.npy") +
+                                     glob.glob(self.data_path + train_folder + "/*.hkl"))
+            val_filenames = sorted(glob.glob(self.data_path + val_folder + "/*.npy") +
+                                   glob.glob(self.data_path + val_folder + "/*.hkl"))
             if debug:
                 train_filenames, val_filenames = train_filenames[:40], val_filenames[:20]
             train_labels = np.load(self.data_path + label_folder + "train_labels.npy")
@@ -92,6 +95,16 @@ class ImageNet_data(object):
             if getattr(self, "zero_copy", True):
                 return src                                          # the loader DMAs straight from this buffer
             np.copyto(out, src.numpy())
+        elif filename.endswith(".hkl"):
+            try:
+                import hickle
+            except ImportError as e:
+                raise RuntimeError("%s: reading the reference's .hkl batches needs the hickle package; convert them to .npy "
+                                   "(uint8 NHWC) instead" % filename) from e
+            arr = np.asarray(hickle.load(filename))
+            if arr.ndim == 4 and arr.shape[0] == self.channels:        # reference layout c01b → b01c
+                arr = np.transpose(arr, (3, 1, 2, 0))
+            np.copyto(out, arr.astype(np.uint8, copy=False))
         else:
             arr = np.load(filename, mmap_mode="r")
             np.copyto(out, arr)
@@ -161,7 +174,7 @@ class ImageNet_data(object):
         src = self.read(item, raw)
         if src is not None:
             raw = src.numpy()
-        arr = (raw.astype(np.float32) - self.rawdata[4]) / 255.0
+        arr = (raw.astype(np.float32) - self.rawdata[4]) / 255.0 / self.rawdata[5]
         arr = crop_and_mirror(arr, mode, model.rand_crop, model.batch_crop_mirror, model.input_width)
         t = torch.from_numpy(arr)
         if model.cuda:
@@ -179,7 +192,7 @@ class ImageNet_data(object):
         from .loader import ParaLoader
         raw_shape = (self.file_batch_size, self.height, self.width, self.channels)
         self.loader = ParaLoader(self.read, device, raw_shape, (input_height, input_width),
-                                 mean=self.rawdata[4], std_scale=1.0 / 255.0, out_dtype=out_dtype,
+                                 mean=self.rawdata[4], std_scale=1.0 / 255.0 / self.rawdata[5], out_dtype=out_dtype,
                                  depth=depth, rand_crop=rand_crop, batch_crop_mirror=batch_crop_mirror)
         return self.loader
 

@@ -57,7 +57,10 @@ class ParaLoader(object):
         self.out_dtype = out_dtype or (torch.bfloat16 if self.cuda else torch.float32)
         N, H, W, C = self.raw_shape
         self.mean = torch.as_tensor(np.asarray(mean, dtype=np.float32)).to(self.device)
-        self.std_scale = float(std_scale)
+        if np.ndim(std_scale) > 0:                       # per-channel 1/(255·img_std) (ref proc_load_mpi.py:99)
+            self.std_scale = torch.as_tensor(np.asarray(std_scale, dtype=np.float32)).to(self.device)
+        else:
+            self.std_scale = float(std_scale)
         pin = self.cuda
         self.host = [torch.empty(self.raw_shape, dtype=torch.uint8, pin_memory=pin) for _ in range(depth)]
         self.host_offs = [torch.empty((N, 2), dtype=torch.int32, pin_memory=pin) for _ in range(depth)]
@@ -136,6 +139,10 @@ class ParaLoader(object):
     def request(self, item, mode=None):
         """Ask for ``item`` to be loaded (the reference's ``icomm.isend(filename, tag=40)``)."""
         req = (item, mode or self.mode)
+        if self._last is not None:
+            # the trainer has already enqueued every read of the batch it was handed last (the copy into its input buffer
+            # happens at the start of its step): mark it consumed NOW, before the producer may pick that slot again
+            self.release(self._last)
         self.outstanding += 1
         if self.threaded:
             self._req.put(req)

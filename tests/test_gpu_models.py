@@ -88,5 +88,5 @@ def test_loader_pipeline_matches_reference_crop():
     torch.cuda.synchronize()
     raw = d.read(d.train_img[0], np.empty((8, 64, 64, 3), np.uint8)).numpy()
     want = ((raw.astype(np.float32) - 127.5) / 255.0 / np.array([0.229, 0.224, 0.225], np.float32))[:, 8:56, 8:56, :]
-    assert np.abs(b.x.float().cpu().numpy() - want).max() < 4e-3
+    assert np.abs(b.x.float().cpu().numpy() - want).max() < 1.2e-2     # bf16 ulp at |x| ~ 2.2
     ld.drain(); d.para_load_close()

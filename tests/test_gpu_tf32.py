@@ -1,0 +1,199 @@
+"""The tf32 precision mode (fp32 storage, tcgen05 kind::tf32 GEMM / implicit conv + fp32 layer kernels) against fp32 PyTorch
+references.  Reference precision: the reference framework computes in fp32 (theanompi/models/layers2.py:380-388, :927-929)."""
+import pytest
+import torch
+
+from theanompi_b200 import ops
+from theanompi_b200.ops import precision
+from theanompi_b200.ops import reference as ref
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True)
+def _tf32_mode():
+    old = precision.precision()
+    precision.set_precision("tf32")
+    yield
+    precision.set_precision(old)
+
+
+def _impl():
+    from theanompi_b200.ops import cuda_impl
+    return cuda_impl
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (256, 384, 512), (200, 136, 324), (128, 4096, 1024), (1000, 72, 132),
+                                   (2304, 2200, 160)])
+def test_gemm_tf32_majors(M, N, K, a_mn, b_mn):
+    ci = _impl()
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device=DEV)
+    B = torch.randn(N, K, device=DEV)
+    want = A.double() @ B.double().t()
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out = ci.gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn, lda=M if a_mn else K, ldb=N if b_mn else K)
+    torch.cuda.synchronize()
+    assert out.dtype == torch.float32
+    assert rel_err(out, want) < 1e-3, rel_err(out, want)           # tf32 operands (10-bit mantissa), fp32 accumulate
+
+
+def test_gemm_tf32_bias_relu_tall_and_splitk():
+    ci = _impl()
+    torch.manual_seed(1)
+    M, N, K = 4232, 256, 192
+    A, B, bias = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV), torch.randn(N, device=DEV)
+    want = torch.relu(A @ B.t() + bias)
+    out = ci.gemm(A, B, M, N, K, bias=bias, bias_mode=1, relu=True, lda=K, ldb=K)
+    assert rel_err(out, want) < 2e-3
+    # split-K wgrad-like problem into a strided fp32 output
+    M, N, K = 96, 364, 8192
+    A = torch.randn(K, M, device=DEV); B = torch.randn(K, 368, device=DEV)
+    want = A.t() @ B[:, :N]
+    out = torch.full((M, N), 7.0, device=DEV)
+    ci.gemm(A, B, M, N, K, a_mn=True, b_mn=True, out=out, lda=M, ldb=368, ldc=N)
+    torch.cuda.synchronize()
+    assert rel_err(out, want) < 2e-3
+
+
+def test_linear_tf32_fwd_bwd():
+    torch.manual_seed(3)
+    x = torch.randn(128, 512, device=DEV).requires_grad_(True)
+    w = (torch.randn(256, 512, device=DEV) * 0.05).requires_grad_(True)
+    b = torch.randn(256, device=DEV).requires_grad_(True)
+    y = ops.linear_bias_act(x, w, b, True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    yr = ref.linear_bias_act(xr, wr, br, True)
+    yr.backward(dy)
+    assert y.dtype == torch.float32
+    assert rel_err(y, yr) < 1e-3 and rel_err(x.grad, xr.grad) < 1e-3 and rel_err(w.grad, wr.grad) < 1e-3 and rel_err(b.grad, br.grad) < 1e-3
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(N=4, H=13, W=13, C=256, O=384, k=3, s=1, p=1, g=1),          # AlexNet conv3
+    dict(N=4, H=27, W=27, C=96, O=256, k=5, s=1, p=2, g=2),           # AlexNet conv2 (two groups, one launch)
+    dict(N=2, H=57, W=57, C=3, O=96, k=11, s=4, p=0, g=1),            # AlexNet conv1 (space-to-depth rewrite), no input grad
+    dict(N=2, H=14, W=14, C=36, O=40, k=3, s=1, p=1, g=1),            # channel counts that are not multiples of 32
+    dict(N=2, H=16, W=16, C=3, O=64, k=3, s=1, p=1, g=1),             # VGG first layer (explicit im2col path)
+    dict(N=2, H=15, W=15, C=32, O=64, k=3, s=2, p=1, g=1),            # strided: dgrad through col2im
+])
+def test_conv_tf32_fwd_bwd(cfg):
+    torch.manual_seed(5)
+    N, H, W, C, O, k, s, p, g = (cfg[n] for n in ("N", "H", "W", "C", "O", "k", "s", "p", "g"))
+    first = C < 4
+    x = torch.randn(N, H, W, C, device=DEV).requires_grad_(not first)
+    if g == 1:
+        w = (torch.randn(O, k, k, C, device=DEV) * 0.1).requires_grad_(True)
+        b = torch.randn(O, device=DEV).requires_grad_(True)
+        y = ops.conv2d_bias_act(x, w, b, s, p, 1, True)
+        params = [w, b]
+    else:
+        ws = [(torch.randn(O // 2, k, k, C // 2, device=DEV) * 0.1).requires_grad_(True) for _ in range(2)]
+        bs = [torch.randn(O // 2, device=DEV).requires_grad_(True) for _ in range(2)]
+        y = ops.conv2d_group2_bias_act(x, ws[0], bs[0], ws[1], bs[1], s, p, True)
+        params = [ws[0], bs[0], ws[1], bs[1]]
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    # fp32 torch reference (NCHW)
+    xr = x.detach().permute(0, 3, 1, 2).clone().requires_grad_(not first)
+    if g == 1:
+        wr = w.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        br = b.detach().clone().requires_grad_(True)
+        yr = torch.relu(torch.nn.functional.conv2d(xr, wr, br, s, p))
+        refs = [wr, br]
+    else:
+        wr = torch.cat([t.detach().permute(0, 3, 1, 2) for t in ws], 0).clone().requires_grad_(True)
+        br = torch.cat([t.detach() for t in bs], 0).clone().requires_grad_(True)
+        yr = torch.relu(torch.nn.functional.conv2d(xr, wr, br, s, p, groups=2))
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        yr.backward(dy.permute(0, 3, 1, 2))
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert y.dtype == torch.float32
+    assert rel_err(y, yr.permute(0, 2, 3, 1)) < 2e-3
+    if not first:
+        assert rel_err(x.grad, xr.grad.permute(0, 2, 3, 1)) < 2e-3
+    if g == 1:
+        assert rel_err(w.grad, wr.grad.permute(0, 2, 3, 1)) < 2e-3 and rel_err(b.grad, br.grad) < 2e-3
+    else:
+        gw = torch.cat([ws[0].grad, ws[1].grad], 0)
+        assert rel_err(gw, wr.grad.permute(0, 2, 3, 1)) < 2e-3
+        assert rel_err(torch.cat([bs[0].grad, bs[1].grad]), br.grad) < 2e-3
+
+
+def test_layer_kernels_fp32():
+    torch.manual_seed(7)
+    x = torch.randn(4, 13, 13, 64, device=DEV).requires_grad_(True)
+    for mode, (k, s, p) in (("max", (3, 2, 0)), ("max", (2, 2, 0)), ("max", (3, 1, 1)), ("avg", (5, 3, 0)), ("avg", (3, 1, 1))):
+        y = ops.pool2d(x, k, s, p, mode)
+        xr = x.detach().clone().requires_grad_(True)
+        yr = ref.pool2d(xr, k, s, p, mode)
+        dy = torch.randn_like(y)
+        y.backward(dy); yr.backward(dy)
+        assert rel_err(y, yr) < 1e-6 and rel_err(x.grad, xr.grad) < 1e-5, (mode, k, s, p)
+        x.grad = None
+    # LRN
+    y = ops.lrn(x, 5, 2.0, 1e-4, 0.75)
+    xr = x.detach().clone().requires_grad_(True)
+    yr, _ = ref.lrn(xr, 5, 2.0, 1e-4, 0.75)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    dxr = ref.lrn_bwd(xr.detach(), dy, 5, 2.0, 1e-4, 0.75)
+    assert rel_err(y, yr) < 1e-4 and rel_err(x.grad, dxr) < 1e-3
+    # softmax + NLL
+    lg = torch.randn(64, 1000, device=DEV).requires_grad_(True)
+    lab = torch.randint(0, 1000, (64,), device=DEV)
+    loss, e1, e5 = ops.softmax_xent(lg, lab)
+    loss.backward()
+    lr_ = lg.detach().clone().requires_grad_(True)
+    lossr = torch.nn.functional.cross_entropy(lr_, lab)
+    lossr.backward()
+    assert abs(float(loss) - float(lossr)) < 1e-4 and rel_err(lg.grad, lr_.grad) < 1e-4
+    # dropout: mask statistics and gradient routing
+    xd = torch.randn(256, 4096, device=DEV).requires_grad_(True)
+    yd = ops.dropout(xd, 0.5, True, layer_id=3)
+    keep = (yd != 0).float().mean().item()
+    assert 0.48 < keep < 0.52
+    yd.backward(torch.ones_like(yd))
+    assert torch.equal(xd.grad != 0, yd != 0)
+
+
+def test_alexnet_tf32_step_and_bf16_agreement():
+    """One AlexNet (small batch) training step in tf32 mode runs on the native kernels with fp32 activations; its loss agrees
+    with the bf16 mode's on the same weights / batch to bf16 accuracy."""
+    from theanompi_b200.models import layers2
+    from theanompi_b200.models.alex_net import AlexNet
+    from theanompi_b200.ops import native
+    from theanompi_b200.utils.recorder import Recorder
+    losses = {}
+    for mode in ("tf32", "bf16"):
+        layers2.reseed(); layers2.Dropout.layers.clear(); layers2.Crop.layers.clear()
+        cfg = dict(verbose=False, rank=0, size=1, device="cuda:0", batch_size=16, file_batch_size=16, dtype=mode, cuda_graph=False,
+                   data_kwargs=dict(n_train_files=4, n_val_files=1, synthetic=True))
+        m = AlexNet(cfg)
+        m.compile_iter_fns("avg")
+        assert m.act_dtype == (torch.float32 if mode == "tf32" else torch.bfloat16)
+        assert (m.arena.H is None) == (mode == "tf32")
+        rec = Recorder(None, 1, "AlexNet", False, device="cuda:0")
+        layers2.Dropout.SetDropoutOff()
+        native.reset_launch_count()
+        m.train_iter(0, rec)
+        torch.cuda.synchronize()
+        layers2.Dropout.SetDropoutOn()
+        assert native.launch_count() > 30
+        losses[mode] = float(rec.train_info["cost"][-1])
+        m.cleanup()
+    precision.set_precision("tf32")
+    assert abs(losses["tf32"] - losses["bf16"]) < 3e-2 * abs(losses["tf32"]), losses

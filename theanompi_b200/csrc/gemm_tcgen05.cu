@@ -29,21 +29,31 @@ std::atomic<unsigned long long> g_launch_count{0};
 namespace gemm {
 
 constexpr int BM = 128;
-constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 320;       // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
 constexpr int NUM_EPI_WARPS = 8;
 
+// Operand element type: __nv_bfloat16 (tcgen05 kind::f16) or float (kind::tf32: fp32 storage, the tensor core reads the top
+// 19 bits).  A k-block is always ONE 128-byte swizzle row per operand row, so the byte geometry of the smem ring, the UMMA
+// descriptors' K-major stepping (32 B per MMA) and the TMA box widths in bytes are identical for both types; what changes is
+// the number of ELEMENTS per k-block / MMA / MN-major atom.
+template <typename T> struct Elem {
+  static constexpr int ESZ = (int)sizeof(T);
+  static constexpr int BK = 128 / ESZ;            // elements per k-block: 64 (bf16) / 32 (tf32)
+  static constexpr int UMMA_K = 32 / ESZ;         // K of one tcgen05.mma: 16 / 8
+  static constexpr int ATOM = 128 / ESZ;          // MN-major: elements of one 128-byte atom row (TMA box width): 64 / 32
+  static constexpr bool TF32 = ESZ == 4;
+};
+
 // MT = number of 128-row sub-tiles a CTA computes per k-block against ONE copy of the B tile (MT = 2: a 256 x BN tile as two
 // MMAs per k-step — half the B (weight) reads per flop, half the per-k-block barrier / issue overhead per flop).
-template <int BN, int MT> struct Cfg {
+template <typename T, int BN, int MT> struct Cfg {
   // persistent kernel, one CTA per SM: operand ring + per-warp epilogue staging chunks + 2 TMEM accumulator stages
-  static constexpr int A_BYTES = MT * BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int A_BYTES = MT * BM * 128;
+  static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   // epilogue staging: each epilogue warp transposes one 32-row x 32-column chunk at a time through its own region
-  // (row pitch = chunk bytes + 16 B: conflict-free 16 B accesses).  MT = 2 tiles are bf16-output only (fprop / dgrad).
-  static constexpr int STAGING_ROW = (MT == 2 ? 32 * 2 : 32 * 4) + 16;
+  // (row pitch = chunk bytes + 16 B: conflict-free 16 B accesses).  bf16 MT = 2 tiles are bf16-output only (fprop / dgrad).
+  static constexpr int STAGING_ROW = ((MT == 2 && sizeof(T) == 2) ? 32 * 2 : 32 * 4) + 16;
   static constexpr int STAGING_BYTES = NUM_EPI_WARPS * 32 * STAGING_ROW;
   static constexpr int SMEM_LIMIT = 232448;                                // 227 KB per CTA
   static constexpr int RING_BUDGET = SMEM_LIMIT - STAGING_BYTES - 1024 /*align slack*/ - 256 /*barriers*/;
@@ -194,12 +204,21 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+template <bool TF32>
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -245,11 +264,14 @@ __device__ __forceinline__ void tile_mn(const Params& p, int rem, int& mti, int&
 //   MMA thread → TMEM accumulator A/B (tmem_full/tmem_empty) → epilogue warps
 // so the epilogue of tile i overlaps the main loop of tile i+1 and all per-CTA setup (TMEM alloc, barrier init,
 // descriptor fetch) is paid once per SM instead of once per tile.
-template <int BN, int MT>
+template <typename T, int BN, int MT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_b0,
-                  const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b1, const Params p) {
-  using C = Cfg<BN, MT>;
+gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant__ CUtensorMap tmap_b0,
+             const __grid_constant__ CUtensorMap tmap_a1, const __grid_constant__ CUtensorMap tmap_b1, const Params p) {
+  using C = Cfg<T, BN, MT>;
+  using E = Elem<T>;
+  constexpr int BK = E::BK, UMMA_K = E::UMMA_K, ATOM = E::ATOM;
+  constexpr int SUB_BYTES = BM * 128;              // one 128-row operand sub-tile of one k-block
   constexpr int TM = MT * BM;                      // rows of a CTA tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B needs 1024B alignment
@@ -318,7 +340,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         }
         int tap = kb0 / p.c_chunks, cc = kb0 - tap * p.c_chunks;
         int r_ = tap / p.cKW, s_ = tap - r_ * p.cKW;
-        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * BM * BK * 2)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * SUB_BYTES)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
         const bool b_t = p.b_mn != 0;
         const int ntaps = p.cKH * p.cKW;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -329,7 +351,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           if (issue_a) {
 #pragma unroll
             for (int u = 0; u < MT; ++u)
-              if (u < n_sub) tma_load_im2col(sa + u * (BM * BK * 2), tma_a, fb, cc * BK, bw0[u], bh0[u], img0[u], s_, r_);
+              if (u < n_sub) tma_load_im2col(sa + u * SUB_BYTES, tma_a, fb, cc * BK, bw0[u], bh0[u], img0[u], s_, r_);
           }
           if (issue_b) {
             if (!b_t) {
@@ -338,8 +360,8 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               // dgrad reads the FORWARD filter [k = out-ch][tap][n = in-ch] in place: MN-major boxes {64 n, 1 tap, 64 k} of
               // the mirrored tap (no flipped / transposed copy of the weights)
 #pragma unroll
-              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j)
-                tma_load_3d(sa + C::A_BYTES + j * (BK * 128), tma_b, fb, n0 + 64 * j, ntaps - 1 - tap, cc * BK);
+              for (int j = 0; j < (BN >= ATOM ? BN / ATOM : 1); ++j)
+                tma_load_3d(sa + C::A_BYTES + j * (BK * 128), tma_b, fb, n0 + ATOM * j, ntaps - 1 - tap, cc * BK);
             }
           }
           if (++cc == p.c_chunks) { cc = 0; ++tap; if (++s_ == p.cKW) { s_ = 0; ++r_; } }
@@ -348,7 +370,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       } else if (p.conv_mode == 2) {
         // ---- conv wgrad: A = dy (MN-major) [64 m x 64 pixels] x2;  B = BN/64 im2col boxes [64 pixels x 64 ch], one per
         //      (filter tap, channel chunk); the k loop walks pixels 64 at a time (W, then H, then N)
-        constexpr int NBOX = (BN >= 64) ? BN / 64 : 1;
+        constexpr int NBOX = (BN >= ATOM) ? BN / ATOM : 1;
         const int total_boxes = p.cKH * p.cKW * p.c_chunks;
         const int w_box0 = nti * NBOX;
         int bc[NBOX], bs[NBOX], br[NBOX];
@@ -357,7 +379,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         for (int j = 0; j < NBOX; ++j) {
           const int box = w_box0 + j;
           const int tapj = box / p.c_chunks, c64 = box - tapj * p.c_chunks;
-          br[j] = tapj / p.cKW; bs[j] = tapj - br[j] * p.cKW; bc[j] = c64 * 64;
+          br[j] = tapj / p.cKW; bs[j] = tapj - br[j] * p.cKW; bc[j] = c64 * ATOM;
           if (box < total_boxes) ++nbox;
         }
         if (skip_b) nbox = 0;
@@ -373,7 +395,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           if (leader) mbar_expect_tx(fb, tx);
           if (issue_a) {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, fb, m0 + 64 * j, pix);
+            for (int j = 0; j < BM / ATOM; ++j) tma_load_2d(sa + j * (BK * 128), tma_a, fb, m0 + ATOM * j, pix);
           }
           if (issue_b) {
             const int cw = qq * p.cS - p.cP, ch = pp * p.cS - p.cP;
@@ -387,7 +409,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
         }
       } else {
         // ---- plain GEMM: K-major operands are one box {64 k, rows}; MN-major operands are 64-wide column boxes {64 mn, 64 k}
-        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * BM * BK * 2)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
+        const uint32_t tx = (skip_a ? 0u : (uint32_t)(n_sub * SUB_BYTES)) + (skip_b ? 0u : (uint32_t)C::B_BYTES);
         const bool a_mn = p.a_mn != 0, b_mn = p.b_mn != 0;
         int k0 = kb0 * BK;
         for (int kb = kb0; kb < kb1; ++kb, k0 += BK) {
@@ -401,10 +423,10 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             for (int u = 0; u < MT; ++u) {
               if (u < n_sub) {
                 if (!a_mn) {
-                  tma_load_2d(sa + u * (BM * BK * 2), tma_a, fb, k0, m0 + u * BM);
+                  tma_load_2d(sa + u * SUB_BYTES, tma_a, fb, k0, m0 + u * BM);
                 } else {
 #pragma unroll
-                  for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + u * (BM * BK * 2) + j * (BK * 128), tma_a, fb, m0 + u * BM + 64 * j, k0);
+                  for (int j = 0; j < BM / ATOM; ++j) tma_load_2d(sa + u * SUB_BYTES + j * (BK * 128), tma_a, fb, m0 + u * BM + ATOM * j, k0);
                 }
               }
             }
@@ -414,7 +436,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               tma_load_2d(sb, tma_b, fb, k0, n0);
             } else {
 #pragma unroll
-              for (int j = 0; j < (BN >= 64 ? BN / 64 : 1); ++j) tma_load_2d(sb + j * (BK * 128), tma_b, fb, n0 + 64 * j, k0);
+              for (int j = 0; j < (BN >= ATOM ? BN / ATOM : 1); ++j) tma_load_2d(sb + j * (BK * 128), tma_b, fb, n0 + ATOM * j, k0);
             }
           }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
@@ -426,14 +448,16 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
     // ===================== MMA issuer (whole warp walks the loop, one elected lane issues) =====================
     const bool leader = elect_one();
     const bool skip_mma = (p.dbg & 4) != 0;
-    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16 (format 1) or tf32 (format 2), majors, N>>3, M>>4
+    constexpr uint32_t kFmt = E::TF32 ? 2u : 1u;
+    const uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16) |
                            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
     // K-major, SW128: 8-row groups 1024 B apart (SBO); advance 32 B per UMMA_K inside the 128 B row.
     // MN-major, SW128: 64-element MN atoms BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
-    //                  advance 16 k-rows = 2048 B per UMMA_K.
-    const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_step = p.a_mn ? 128u : 2u;
-    const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_step = p.b_mn ? 128u : 2u;
+    //                  advance UMMA_K k-rows = UMMA_K * 128 B per MMA (2048 B bf16, 1024 B tf32).
+    constexpr uint32_t kMnStep = (uint32_t)(UMMA_K * 128) >> 4;
+    const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_step = p.a_mn ? kMnStep : 2u;
+    const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_step = p.b_mn ? kMnStep : 2u;
     const uint64_t adesc_base = make_smem_desc(smem_base, a_lbo, 1024u);
     const uint64_t bdesc_base = make_smem_desc(smem_base + C::A_BYTES, b_lbo, 1024u);
     int stage = 0; uint32_t phase = 0;
@@ -458,7 +482,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             for (int k = 0; k < BK / UMMA_K; ++k) {
 #pragma unroll
               for (int u = 0; u < MT; ++u)             // the MT sub-tiles share the B descriptor
-                umma_bf16(tmem_acc + (uint32_t)(u * BN), adesc0 + (uint64_t)(u * ((BM * BK * 2) >> 4)) + (uint64_t)(a_step * k),
+                umma_ss<E::TF32>(tmem_acc + (uint32_t)(u * BN), adesc0 + (uint64_t)(u * (SUB_BYTES >> 4)) + (uint64_t)(a_step * k),
                           bdesc0 + (uint64_t)(b_step * k), idesc, accumulate);
               accumulate = 1u;
             }
@@ -498,19 +522,9 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
       int mti, nti;
       tile_mn(p, rem, mti, nti);
       const int m0 = mti * TM;
-      int n0 = nti * BN, n_end = p.N;                // global column of tile column cc is n0 + cc
-      if (p.conv_mode == 2) {
-        // wgrad: every 64-column box of the tile is one (filter tap, 64-channel chunk); this warp's columns [col0, col0+64)
-        // are exactly one box, which lands at column tap*Cg + c64*64 of dW.
-        const int box = nti * (BN >= 64 ? BN / 64 : 1) + col0 / 64;
-        if (box < p.cKH * p.cKW * p.c_chunks) {
-          const int tap = box / p.c_chunks, c64 = box - tap * p.c_chunks;
-          n0 = tap * p.cCg + c64 * 64 - col0;
-          n_end = tap * p.cCg + min(p.cCg, c64 * 64 + 64);
-        } else {
-          n0 = 0; n_end = 0;
-        }
-      }
+      const int n0 = nti * BN, n_end = p.N;          // global column of tile column cc is n0 + cc (GEMM / conv fprop)
+      // wgrad (conv_mode 2): every ATOM-column box of the tile is one (filter tap, ATOM-channel chunk) and lands at column
+      // tap*Cg + chunk*ATOM of dW — resolved per 32-column chunk below (a chunk never straddles two boxes)
       // bias prefetch BEFORE waiting for the accumulator (hidden behind the main loop): per-column bias — lane j holds the
       // bias of column (chunk base + j), broadcast later with shuffles; per-row bias — one value per sub-tile row.
       float bias_m0 = 0.f, bias_m1 = 0.f;
@@ -552,7 +566,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
           }
           if (mbase >= p.M) continue;                // warp-uniform: whole sub-tile out of range
-          const int nb = n0 + cc;
+          int nb = n0 + cc, n_end_c = n_end;
+          if (p.conv_mode == 2) {
+            const int box = nti * (BN >= ATOM ? BN / ATOM : 1) + cc / ATOM;
+            if (box < p.cKH * p.cKW * p.c_chunks) {
+              const int tap = box / p.c_chunks, cch = box - tap * p.c_chunks;
+              nb = tap * p.cCg + cch * ATOM + (cc % ATOM);
+              n_end_c = tap * p.cCg + min(p.cCg, cch * ATOM + ATOM);
+            } else {
+              nb = 0; n_end_c = 0;
+            }
+          }
           const float bias_sel = (c == 0) ? bias_c0 : bias_c1;
           float v[32];
           if (p.bias_mode == 1) {
@@ -569,7 +593,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
           }
           // Fast path: chunk fully in range and 16-byte aligned → transposed through smem, coalesced 16 B row-segment
           // stores (plain, or vector reductions red.global.add.v4.f32 for split-K).
-          const bool staged = (nb + 32 <= n_end) && ld_ok && (((reinterpret_cast<uintptr_t>(Cg_ptr) + (long long)nb * esz) % 16) == 0);
+          const bool staged = (nb + 32 <= n_end_c) && ld_ok && (((reinterpret_cast<uintptr_t>(Cg_ptr) + (long long)nb * esz) % 16) == 0);
           if (staged) {
             uint8_t* dst = wstage + (size_t)lane * pitch;
             if (p.out_bf16) {
@@ -611,17 +635,17 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
             __syncwarp();                                              // staging region is free for the next chunk
             continue;
           }
-          if (!m_ok || nb >= n_end) continue;
-          const bool full = (nb + 32 <= n_end);
+          if (!m_ok || nb >= n_end_c) continue;
+          const bool full = (nb + 32 <= n_end_c);
           if (p.rs_world > 0) {
             const long long e0 = p.rs_e0 + (long long)m * p.ldc + nb;
             for (int j = 0; j < 32; ++j) {
-              if (full || nb + j < n_end) { bool local; red_add_sys_f32(rs_addr(p, e0 + j, local), v[j]); }
+              if (full || nb + j < n_end_c) { bool local; red_add_sys_f32(rs_addr(p, e0 + j, local), v[j]); }
             }
           } else if (p.atomic_out) {
             float* dst = reinterpret_cast<float*>(Cg_ptr) + (long long)m * p.ldc + nb;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (full || nb + j < n_end) atomicAdd(dst + j, v[j]);
+            for (int j = 0; j < 32; ++j) if (full || nb + j < n_end_c) atomicAdd(dst + j, v[j]);
           } else if (p.out_bf16) {
             __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cg_ptr) + (long long)m * p.ldc + nb;
             if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -629,7 +653,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               for (int j = 0; j < 32; j += 8) { bf16x8 pk = pack8(v + j); *reinterpret_cast<bf16x8*>(dst + j) = pk; }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = f_to_bf16(v[j]);
+              for (int j = 0; j < 32; ++j) if (nb + j < n_end_c) dst[j] = f_to_bf16(v[j]);
             }
           } else {
             float* dst = reinterpret_cast<float*>(Cg_ptr) + (long long)m * p.ldc + nb;
@@ -638,7 +662,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_cons
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (nb + j < n_end) dst[j] = v[j];
+              for (int j = 0; j < 32; ++j) if (nb + j < n_end_c) dst[j] = v[j];
             }
           }
         }
@@ -669,23 +693,24 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2-D bf16 tensor map: dims {inner, outer}, row pitch in bytes, box {64, box_outer}, 128B swizzle, zero OOB fill.
-static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer) {
+// 2-D tensor map (bf16 or fp32 elements): dims {inner, outer}, row pitch in bytes, box {128 bytes, box_outer}, 128B swizzle,
+// zero OOB fill.
+static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer, int esz = 2) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand base must be 16B aligned");
   if ((pitch_bytes & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand row pitch must be a multiple of 16 bytes");
-  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t>;
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{ptr, inner, outer, pitch_bytes, box_outer};
+  Key key{ptr, inner, outer, pitch_bytes, box_outer, esz};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_bytes};
-  cuuint32_t box[2] = {64u, box_outer};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
@@ -715,31 +740,32 @@ static int choose_splits(int tiles, int num_kb, int sms) {
   return best;
 }
 
-template <int BN, int MT>
+template <typename T, int BN, int MT>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int splits, cudaStream_t st,
                    const CUtensorMap* ta1 = nullptr, const CUtensorMap* tb1 = nullptr) {
-  using C = Cfg<BN, MT>;
+  using C = Cfg<T, BN, MT>;
   p.dbg = g_dbg;
   if (!ta1) { p.groups = 1; p.C1 = nullptr; p.bias1 = nullptr; }
   static bool attr_set = false;
   if (!attr_set) {
-    check_cuda(cudaFuncSetAttribute(gemm_bf16_tcgen05<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
+    check_cuda(cudaFuncSetAttribute(gemm_tcgen05<T, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES), "gemm smem attr");
     attr_set = true;
   }
-  if (MT == 2 && !p.out_bf16) throw std::runtime_error("tmpi_native: 256-row GEMM tiles are bf16-output only");
+  if (MT == 2 && sizeof(T) == 2 && !p.out_bf16) throw std::runtime_error("tmpi_native: 256-row bf16 GEMM tiles are bf16-output only");
+  if (sizeof(T) == 4 && p.out_bf16) throw std::runtime_error("tmpi_native: the tf32 path stores fp32");
   const long long total = (long long)p.mt * p.nt * splits * p.groups;
   const int grid = (int)std::min<long long>(total, (long long)sm_count());
-  gemm_bf16_tcgen05<BN, MT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, p);
+  gemm_tcgen05<T, BN, MT><<<grid, NUM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, ta1 ? *ta1 : ta, tb1 ? *tb1 : tb, p);
   count_launch();
-  TMPI_CHECK_LAUNCH("gemm_bf16_tcgen05"); ::tmpi::check_capture(st, "gemm_bf16_tcgen05");
+  TMPI_CHECK_LAUNCH("gemm_tcgen05"); ::tmpi::check_capture(st, "gemm_tcgen05");
 }
 
 // 256-row tiles (MT = 2) when the output is bf16 (no split-K) and the wave arithmetic favours them: a tall tile costs ~1.7x a
 // 128-row tile (measured: conv3 fprop 21.5 us vs 12.8 us per wave — the B tile and the per-k-block overhead are shared), so
 // it wins unless halving the tile count wastes most of a wave (conv3 dgrad: 170 tall tiles = 2 waves vs 338 = 3 short ones).
-static bool use_tall_tiles(long long M, int nt, int out_bf16, int sms) {
+static bool use_tall_tiles(long long M, int nt, int eligible, int sms) {
   static const bool enabled = [] { const char* e = getenv("TMPI_GEMM_TALL"); return !(e && e[0] == '0'); }();
-  if (!enabled || !out_bf16 || M < 2 * BM) return false;
+  if (!enabled || !eligible || M < 2 * BM) return false;
   const long long t1 = ((M + BM - 1) / BM) * nt, t2 = ((M + 2 * BM - 1) / (2 * BM)) * nt;
   const long long w1 = (t1 + sms - 1) / sms, w2 = (t2 + sms - 1) / sms;
   return w2 * 17 <= w1 * 10;
@@ -804,14 +830,19 @@ int gemm_plan_tall(long long M, int nt, int out_bf16, int sms) { return gemm::us
 //   a_mn == 0: A is [M, K] with row pitch lda (elements);  a_mn == 1: A is [K, M] with row pitch lda.
 //   b_mn == 0: B is [N, K] with row pitch ldb;             b_mn == 1: B is [K, N] with row pitch ldb.
 //   bn_hint: 0 = auto, else 32/64/128.  splitk: 0 = auto, 1 = none, >1 = forced (fp32 output only, no bias/relu).
-void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
-               long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
-               cudaStream_t st) {
-  using namespace gemm;
+//   T = __nv_bfloat16: bf16 operands (kind::f16), bf16 or fp32 output.  T = float: fp32 operands (kind::tf32), fp32 output.
+namespace gemm {
+template <typename T>
+static void gemm_host(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
+                      long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
+                      cudaStream_t st) {
+  using E = Elem<T>;
+  constexpr int BK = E::BK, ATOM = E::ATOM, ESZ = E::ESZ;
   if (M <= 0 || N <= 0 || K <= 0) return;
   const int sms = sm_count();
   const int mt = (M + BM - 1) / BM;
-  const bool can_split = (!out_bf16) && bias_mode == 0 && !relu;
+  const bool fused_epi = bias_mode != 0 || relu;
+  const bool can_split = (!out_bf16) && !fused_epi;
   int BN = bn_hint;
   if (BN == 0) {
     BN = 128;
@@ -836,7 +867,9 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
   Params p;
   p.C = C; p.bias = bias; p.alpha = alpha; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.a_mn = a_mn; p.b_mn = b_mn;
   p.out_bf16 = out_bf16; p.bias_mode = bias ? bias_mode : 0; p.relu = relu; p.kb_per_split = kb_per; p.atomic_out = splits > 1;
-  const bool tall = splits == 1 && BN >= 64 && use_tall_tiles(M, nt, out_bf16, sms);
+  // tall tiles: bf16 path — bf16 outputs (fprop / dgrad); tf32 path — any un-split output (activations are fp32 there)
+  const int tall_ok = ESZ == 2 ? out_bf16 : 1;
+  const bool tall = splits == 1 && BN >= 64 && use_tall_tiles(M, nt, tall_ok, sms);
   p.mt = tall ? (M + 2 * BM - 1) / (2 * BM) : mt; p.nt = nt; p.splits = splits; p.num_kb = num_kb; p.conv_mode = 0;
   p.group_m = (p.mt > 12 && nt > 12) ? (tall ? 8 : 12) : 0;
   p.cHo = p.cWo = p.cS = p.cP = p.cKH = p.cKW = p.cCg = p.c_chunks = 0;
@@ -849,14 +882,23 @@ void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, 
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
     check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");
   }
-  CUtensorMap ta = a_mn ? make_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64u)
-                        : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, (uint32_t)BM);
-  CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64u)
-                        : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, (uint32_t)BN);
-  if (tall) { if (BN == 128) launch<128, 2>(ta, tb, p, splits, st); else launch<64, 2>(ta, tb, p, splits, st); }
-  else if (BN == 128) launch<128, 1>(ta, tb, p, splits, st);
-  else if (BN == 64) launch<64, 1>(ta, tb, p, splits, st);
-  else launch<32, 1>(ta, tb, p, splits, st);
+  CUtensorMap ta = a_mn ? make_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * ESZ, (uint32_t)BK, ESZ)
+                        : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * ESZ, (uint32_t)BM, ESZ);
+  CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * ESZ, (uint32_t)BK, ESZ)
+                        : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * ESZ, (uint32_t)BN, ESZ);
+  (void)ATOM;
+  if (tall) { if (BN == 128) launch<T, 128, 2>(ta, tb, p, splits, st); else launch<T, 64, 2>(ta, tb, p, splits, st); }
+  else if (BN == 128) launch<T, 128, 1>(ta, tb, p, splits, st);
+  else if (BN == 64) launch<T, 64, 1>(ta, tb, p, splits, st);
+  else launch<T, 32, 1>(ta, tb, p, splits, st);
+}
+}  // namespace gemm
+
+void gemm_bf16(const void* A, const void* B, void* C, const float* bias, int M, int N, int K, long long lda, long long ldb,
+               long long ldc, int a_mn, int b_mn, int out_bf16, int bias_mode, int relu, float alpha, int bn_hint, int splitk,
+               cudaStream_t st, int tf32) {
+  if (tf32) gemm::gemm_host<float>(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, 0, bias_mode, relu, alpha, bn_hint, splitk, st);
+  else gemm::gemm_host<__nv_bfloat16>(A, B, C, bias, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_bf16, bias_mode, relu, alpha, bn_hint, splitk, st);
 }
 
 // ------------------------------------------------------------------ implicit-GEMM convolution (TMA im2col)
@@ -879,124 +921,118 @@ static PFN_encodeIm2col get_encode_im2col() {
 }
 
 // NHWC activation (channel slice [c_off, c_off+Cg) of a tensor with Ctot channels) as an im2col tensor map:
-// box = pixels x 64 channels, 128 B swizzle, zero fill for padding / out-of-range pixels / channels >= Cg.
-static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int S, int P, int pixels) {
-  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(x) + c_off;
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (Ctot % 8) != 0) throw std::runtime_error("tmpi_native: im2col operand must be 16B aligned");
-  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int, int, int>;
+// box = pixels x 128 bytes of channels (64 bf16 / 32 fp32), 128 B swizzle, zero fill for padding / out-of-range pixels /
+// channels >= Cg.
+static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int S, int P, int pixels,
+                                   int esz) {
+  const char* base = reinterpret_cast<const char*>(x) + (size_t)c_off * esz;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((Ctot * esz) % 16) != 0) throw std::runtime_error("tmpi_native: im2col operand must be 16B aligned");
+  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{base, N, H, W, Ctot, Cg, KH, KW, S, P, pixels};
+  Key key{base, N, H, W, Ctot, Cg, KH, KW, S, P, pixels, esz};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)Cg, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)Ctot * 2, (cuuint64_t)W * Ctot * 2, (cuuint64_t)H * W * Ctot * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)Ctot * esz, (cuuint64_t)W * Ctot * esz, (cuuint64_t)H * W * Ctot * esz};
   int lower[2] = {-P, -P};
   int upper[2] = {P - (KW - 1), P - (KH - 1)};
   cuuint32_t estr[4] = {1u, (cuuint32_t)S, (cuuint32_t)S, 1u};
-  CUresult r = get_encode_im2col()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(base), dims, strides, lower, upper,
-                                   64u, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = get_encode_im2col()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base),
+                                   dims, strides, lower, upper, (cuuint32_t)(128 / esz), (cuuint32_t)pixels, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeIm2col failed, code " + std::to_string((int)r));
   if (cache.size() > 4096) cache.clear();
   cache[key] = m;
   return m;
 }
 
-// weights [O][KH*KW][Cg] (bf16, contiguous) as a 3-D tiled map, box {64 ch, 1 tap, box_o out-channels}
-static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o, int box_c = 64) {
-  if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || (Cg % 8) != 0) throw std::runtime_error("tmpi_native: conv weights must be 16B aligned, C % 8 == 0");
-  using Key = std::tuple<const void*, int, int, int, int, int>;
+// weights [O][KH*KW][Cg] (contiguous) as a 3-D tiled map, box {box_c ch, 1 tap, box_o out-channels}
+static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o, int box_c, int esz) {
+  if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || ((Cg * esz) % 16) != 0) throw std::runtime_error("tmpi_native: conv weights must be 16B aligned, C * esz % 16 == 0");
+  using Key = std::tuple<const void*, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{w, O, taps, Cg, box_o, box_c};
+  Key key{w, O, taps, Cg, box_o, box_c, esz};
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   CUtensorMap m;
   cuuint64_t dims[3] = {(cuuint64_t)Cg, (cuuint64_t)taps, (cuuint64_t)O};
-  cuuint64_t strides[2] = {(cuuint64_t)Cg * 2, (cuuint64_t)taps * Cg * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)Cg * esz, (cuuint64_t)taps * Cg * esz};
   cuuint32_t box[3] = {(cuuint32_t)box_c, 1u, (cuuint32_t)box_o};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = get_encode()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled(3D weights) failed, code " + std::to_string((int)r));
   if (cache.size() > 4096) cache.clear();
   cache[key] = m;
   return m;
 }
-}  // namespace gemm
 
-// y[N*Ho*Wo, O] (ld = ldc, bf16) = relu(conv(x[.., c_off:c_off+Cg], w[O][KH][KW][Cg]) + bias)   — no col matrix in memory
+// y[N*Ho*Wo, O] (ld = ldc) = relu(conv(x[.., c_off:c_off+Cg], w[O][KH][KW][Cg]) + bias)   — no col matrix in memory
 // dgrad = 1: the same kernel computes the input gradient — x is dy, (Cg, O) are (#dy channels, #dx channels) and w is the
 // FORWARD filter [Cg][KH][KW][O], read mirrored and transposed by the TMA loads (stride-1 convolutions only).
 // ngroups = 2: both groups of a grouped convolution in ONE persistent launch (group g reads channel slice c_off[g] of x,
 // filter w[g], writes y[g] / adds bias[g]) — their tiles fill the machine together instead of two under-filled waves.
+template <typename T>
 static void conv_fprop_groups(int ngroups, const void* x, const int* c_off, const void* const* w, void* const* y, const float* const* bias,
                               int N, int H, int W, int Ctot, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
                               int relu, int out_bf16, int dgrad, cudaStream_t st) {
-  using namespace gemm;
+  using E = Elem<T>;
+  constexpr int BK = E::BK, ATOM = E::ATOM, ESZ = E::ESZ;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0 || O <= 0) return;
   if (M >= (1LL << 31)) throw std::runtime_error("conv_fprop: too many output pixels");
+  if (ESZ == 4) out_bf16 = 0;
   const int BN = O > 64 ? 128 : 64;
   Params p;
   p.C = y[0]; p.bias = bias[0]; p.alpha = 1.f; p.M = (int)M; p.N = O; p.K = KH * KW * Cg; p.ldc = ldc; p.a_mn = 0; p.b_mn = dgrad ? 1 : 0;
   p.groups = ngroups; p.C1 = ngroups > 1 ? y[1] : nullptr; p.bias1 = ngroups > 1 ? bias[1] : nullptr;
   p.out_bf16 = out_bf16; p.bias_mode = bias[0] ? 1 : 0; p.relu = relu; p.atomic_out = 0;
   if (ngroups > 1 && ((bias[0] == nullptr) != (bias[1] == nullptr))) throw std::runtime_error("conv_fprop: both groups need a bias or none");
-  if (dgrad && (S != 1 || (O % 8) != 0)) throw std::runtime_error("conv dgrad through the fprop kernel needs stride 1 and C % 8 == 0");
+  if (dgrad && (S != 1 || ((O * ESZ) % 16) != 0)) throw std::runtime_error("conv dgrad through the fprop kernel needs stride 1 and 16-byte channel rows");
   p.nt = (O + BN - 1) / BN; p.splits = 1;
-  const bool tall = use_tall_tiles(M, p.nt * ngroups, out_bf16, sm_count());
+  const bool tall = use_tall_tiles(M, p.nt * ngroups, ESZ == 2 ? out_bf16 : 1, sm_count());
   p.mt = tall ? (int)((M + 2 * BM - 1) / (2 * BM)) : (int)((M + BM - 1) / BM);
   p.group_m = 0;
   p.conv_mode = 1; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + BK - 1) / BK;
   p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
   CUtensorMap ta[2], tb[2];
   for (int g = 0; g < ngroups; ++g) {
-    ta[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BM);
-    tb[g] = dgrad ? make_weight_map(w[g], Cg, KH * KW, O, 64, 64) : make_weight_map(w[g], O, KH * KW, Cg, BN);
+    ta[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BM, ESZ);
+    tb[g] = dgrad ? make_weight_map(w[g], Cg, KH * KW, O, BK, ATOM, ESZ) : make_weight_map(w[g], O, KH * KW, Cg, BN, BK, ESZ);
   }
   const CUtensorMap* a1 = ngroups > 1 ? &ta[1] : nullptr;
   const CUtensorMap* b1 = ngroups > 1 ? &tb[1] : nullptr;
-  if (tall) { if (BN == 128) launch<128, 2>(ta[0], tb[0], p, 1, st, a1, b1); else launch<64, 2>(ta[0], tb[0], p, 1, st, a1, b1); }
-  else if (BN == 128) launch<128, 1>(ta[0], tb[0], p, 1, st, a1, b1);
-  else launch<64, 1>(ta[0], tb[0], p, 1, st, a1, b1);
+  if (tall) { if (BN == 128) launch<T, 128, 2>(ta[0], tb[0], p, 1, st, a1, b1); else launch<T, 64, 2>(ta[0], tb[0], p, 1, st, a1, b1); }
+  else if (BN == 128) launch<T, 128, 1>(ta[0], tb[0], p, 1, st, a1, b1);
+  else launch<T, 64, 1>(ta[0], tb[0], p, 1, st, a1, b1);
 }
 
-void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
-                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st) {
-  const void* ws[1] = {w}; void* ys[1] = {y}; const float* bs[1] = {bias};
-  conv_fprop_groups(1, x, &c_off, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
-}
-
-void conv_fprop2_bf16(const void* x, const void* w0, const void* w1, void* y0, void* y1, const float* bias0, const float* bias1, int N, int H,
-                      int W, int Ctot, int c_off0, int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
-                      int relu, int out_bf16, int dgrad, cudaStream_t st) {
-  const int co[2] = {c_off0, c_off1}; const void* ws[2] = {w0, w1}; void* ys[2] = {y0, y1}; const float* bs[2] = {bias0, bias1};
-  conv_fprop_groups(2, x, co, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
-}
-
-// dw[O][KH*KW][Cg] (fp32, contiguous) = sum over pixels dy[pix, o] * im2col(x)[pix, (tap, c)]   (dy: [M, O] bf16, row pitch ldy)
+// dw[O][KH*KW][Cg] (fp32, contiguous) = sum over pixels dy[pix, o] * im2col(x)[pix, (tap, c)]   (dy: [M, O], row pitch ldy)
 // ngroups = 2: both groups in one launch (dy[g] = the group's channel slice of the output gradient, x slice c_off[g], dw[g]).
+template <typename T>
 static void conv_wgrad_groups(int ngroups, const void* const* dy, const void* x, void* const* dw, const int* c_off, int N, int H, int W,
                               int Ctot, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
-  using namespace gemm;
+  using E = Elem<T>;
+  constexpr int BK = E::BK, ATOM = E::ATOM, ESZ = E::ESZ;
   const long long M = (long long)N * Ho * Wo;
   if (M <= 0 || O <= 0) return;
   if (M >= (1LL << 31)) throw std::runtime_error("conv_wgrad: too many output pixels");
   const int sms = sm_count();
-  const int BN = 128;                                  // two (tap, 64-channel) boxes per n-tile: halves the re-reads of dy
+  const int BN = 128;                                  // BN / ATOM (tap, channel-chunk) boxes per n-tile: fewer re-reads of dy
   Params p;
   p.C = dw[0]; p.bias = nullptr; p.alpha = 1.f; p.M = O; p.N = KH * KW * Cg; p.K = (int)M; p.ldc = (long long)KH * KW * Cg; p.a_mn = 1; p.b_mn = 1;
   p.groups = ngroups; p.C1 = ngroups > 1 ? dw[1] : nullptr; p.bias1 = nullptr;
   p.out_bf16 = 0; p.bias_mode = 0; p.relu = 0;
   p.group_m = 0;
-  p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + 63) / 64;
-  p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / 64 - 1) / (BN / 64);
+  p.conv_mode = 2; p.cHo = Ho; p.cWo = Wo; p.cS = S; p.cP = P; p.cKH = KH; p.cKW = KW; p.cCg = Cg; p.c_chunks = (Cg + ATOM - 1) / ATOM;
+  p.mt = (O + BM - 1) / BM; p.nt = (KH * KW * p.c_chunks + BN / ATOM - 1) / (BN / ATOM);
   p.num_kb = (int)((M + BK - 1) / BK);
   int splits = choose_splits(p.mt * p.nt * ngroups, p.num_kb, sms);
   p.kb_per_split = (p.num_kb + splits - 1) / splits;
@@ -1005,22 +1041,40 @@ static void conv_wgrad_groups(int ngroups, const void* const* dy, const void* x,
   CUtensorMap ta[2], tb[2];
   for (int g = 0; g < ngroups; ++g) {
     if (splits > 1) check_cuda(cudaMemsetAsync(dw[g], 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
-    ta[g] = make_tmap(dy[g], (uint64_t)O, (uint64_t)M, (uint64_t)ldy * 2, 64u);
-    tb[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BK);
+    ta[g] = make_tmap(dy[g], (uint64_t)O, (uint64_t)M, (uint64_t)ldy * ESZ, (uint32_t)BK, ESZ);
+    tb[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BK, ESZ);
   }
-  launch<128, 1>(ta[0], tb[0], p, splits, st, ngroups > 1 ? &ta[1] : nullptr, ngroups > 1 ? &tb[1] : nullptr);
+  launch<T, 128, 1>(ta[0], tb[0], p, splits, st, ngroups > 1 ? &ta[1] : nullptr, ngroups > 1 ? &tb[1] : nullptr);
+}
+}  // namespace gemm
+
+void conv_fprop_bf16(const void* x, const void* w, void* y, const float* bias, int N, int H, int W, int Ctot, int c_off, int Cg, int KH,
+                     int KW, int Ho, int Wo, int S, int P, int O, long long ldc, int relu, int out_bf16, int dgrad, cudaStream_t st, int tf32) {
+  const void* ws[1] = {w}; void* ys[1] = {y}; const float* bs[1] = {bias};
+  if (tf32) gemm::conv_fprop_groups<float>(1, x, &c_off, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, 0, dgrad, st);
+  else gemm::conv_fprop_groups<__nv_bfloat16>(1, x, &c_off, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
+}
+
+void conv_fprop2_bf16(const void* x, const void* w0, const void* w1, void* y0, void* y1, const float* bias0, const float* bias1, int N, int H,
+                      int W, int Ctot, int c_off0, int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldc,
+                      int relu, int out_bf16, int dgrad, cudaStream_t st, int tf32) {
+  const int co[2] = {c_off0, c_off1}; const void* ws[2] = {w0, w1}; void* ys[2] = {y0, y1}; const float* bs[2] = {bias0, bias1};
+  if (tf32) gemm::conv_fprop_groups<float>(2, x, co, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, 0, dgrad, st);
+  else gemm::conv_fprop_groups<__nv_bfloat16>(2, x, co, ws, ys, bs, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldc, relu, out_bf16, dgrad, st);
 }
 
 void conv_wgrad_bf16(const void* dy, const void* x, void* dw, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho,
-                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+                     int Wo, int S, int P, int O, long long ldy, cudaStream_t st, int tf32) {
   const void* dys[1] = {dy}; void* dws[1] = {dw};
-  conv_wgrad_groups(1, dys, x, dws, &c_off, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
+  if (tf32) gemm::conv_wgrad_groups<float>(1, dys, x, dws, &c_off, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
+  else gemm::conv_wgrad_groups<__nv_bfloat16>(1, dys, x, dws, &c_off, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
 }
 
 void conv_wgrad2_bf16(const void* dy0, const void* dy1, const void* x, void* dw0, void* dw1, int N, int H, int W, int Ctot, int c_off0,
-                      int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st) {
+                      int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st, int tf32) {
   const void* dys[2] = {dy0, dy1}; void* dws[2] = {dw0, dw1}; const int co[2] = {c_off0, c_off1};
-  conv_wgrad_groups(2, dys, x, dws, co, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
+  if (tf32) gemm::conv_wgrad_groups<float>(2, dys, x, dws, co, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
+  else gemm::conv_wgrad_groups<__nv_bfloat16>(2, dys, x, dws, co, N, H, W, Ctot, Cg, KH, KW, Ho, Wo, S, P, O, ldy, st);
 }
 
 }  // namespace tmpi

@@ -71,7 +71,13 @@ class ModelBase(object):
         self.no_paraload = config.get("no_paraload", False)
         self.device = pick_device(config)
         self.cuda = self.device.type == "cuda"
-        self.act_dtype = torch.bfloat16 if self.cuda else torch.float32
+        # compute precision of the native path: 'bf16' (bf16 operands, fp32 accumulate / master weights) or 'tf32' (fp32 storage
+        # end to end, tcgen05 kind::tf32 — the reference's precision class); see ops/precision.py
+        from ..ops import precision
+        if config.get("dtype"):
+            precision.set_precision(config["dtype"])
+        self.precision = precision.precision()
+        self.act_dtype = precision.act_dtype() if self.cuda else torch.float32
         # "auto" (default on CUDA): capture the whole step into a CUDA graph, fall back to eager launches if the model's
         # step cannot be captured (host-side control flow, library calls that synchronise, …)
         cg = config.get("cuda_graph", "auto")
@@ -118,7 +124,7 @@ class ModelBase(object):
         allocator = self.config.get("arena_allocator")
         self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta,
                                with_recv=allocator is not None, allocator=allocator,
-                               shadow=self.config.get("_arena_shadow"))
+                               shadow=False if self.precision == "tf32" else self.config.get("_arena_shadow"))
         self.shared_lr = SharedScalar(self.arena.hyper, 0, self.base_lr)
         self.sgd = FlatSGD(self.arena, self.mu, self.use_nesterov_momentum, self.use_momentum)
         B = self.batch_size

@@ -18,10 +18,25 @@ import os
 
 import torch
 
-from . import native
+from . import native, precision
 
 _STEP = {}          # device index -> int64[1] step counter used by the dropout Philox stream
 BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def ADT():
+    """Activation dtype of the active precision mode (bf16, or fp32 for the tf32 path)."""
+    return precision.act_dtype()
+
+
+def _is32(t):
+    return t.dtype == F32
+
+
+def _al(t):
+    """Elements per 16 bytes (TMA / vector alignment unit): 8 for bf16, 4 for fp32."""
+    return 16 // t.element_size()
 
 
 def L():
@@ -51,37 +66,42 @@ def advance_step(device):
 
 
 def _bf(t):
-    return t if t.dtype == BF16 else t.to(BF16)
+    """Cast to the activation dtype of the active precision mode (no-op on the hot path: layers already produce it)."""
+    d = ADT()
+    return t if t.dtype == d else t.to(d)
 
 
 def _rows8(t2d):
-    """Return a 2-D bf16 tensor whose row pitch is a multiple of 8 elements (TMA: 16 B) —
-    the tensor itself when it already is, else a zero-padded copy (rare, tiny shapes)."""
+    """Return a 2-D tensor whose row pitch is a multiple of 16 bytes (TMA rule) — the tensor itself when it already is, else
+    a zero-padded copy (rare, tiny shapes)."""
     assert t2d.dim() == 2
-    if t2d.stride(1) == 1 and t2d.stride(0) % 8 == 0 and t2d.data_ptr() % 16 == 0:
+    al = _al(t2d)
+    if t2d.stride(1) == 1 and t2d.stride(0) % al == 0 and t2d.data_ptr() % 16 == 0:
         return t2d, t2d.stride(0)
     R, C = t2d.shape
-    ld = (C + 7) // 8 * 8
-    out = torch.zeros((R, ld), dtype=BF16, device=t2d.device)
+    ld = (C + al - 1) // al * al
+    out = torch.zeros((R, ld), dtype=t2d.dtype, device=t2d.device)
     out[:, :C] = t2d
     return out, ld
 
 
 # --------------------------------------------------------------------------- GEMM
-def gemm(a, b, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=BF16, bias=None, bias_mode=0,
+def gemm(a, b, M, N, K, a_mn=False, b_mn=False, out=None, out_dtype=None, bias=None, bias_mode=0,
          relu=False, alpha=1.0, lda=None, ldb=None, ldc=None, bn=0, splitk=0):
     """``out[M,N] = alpha * op(a) @ op(b) (+bias)(ReLU)``; ``a``/``b`` are bf16 tensors whose
     storage is described by (major flag, leading dimension)."""
     dev = a.device
+    tf32 = _is32(a)
+    assert a.dtype == b.dtype, "GEMM operands must share a dtype"
     if out is None:
-        out = torch.empty((M, N), dtype=out_dtype, device=dev)
+        out = torch.empty((M, N), dtype=(F32 if tf32 else (out_dtype or BF16)), device=dev)
     if ldc is None:
         ldc = out.stride(0) if out.dim() == 2 else N
     if bias is not None:
         assert bias.dtype == torch.float32
     L().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), _p(bias), int(M), int(N), int(K), int(lda), int(ldb),
                   int(ldc), int(bool(a_mn)), int(bool(b_mn)), int(out.dtype == BF16), int(bias_mode), int(bool(relu)),
-                  float(alpha), int(bn), int(splitk), _st(a))
+                  float(alpha), int(bn), int(splitk), _st(a), int(tf32))
     return out
 
 
@@ -93,6 +113,10 @@ def linear_bias_act(x, w, b, relu=True):
     xa, lda = _rows8(x2)
     wa, ldb = _rows8(_bf(w))
     bias = b.float() if b is not None and b.dtype != torch.float32 else b
+    if FC_SPLITK and B_ <= 128 and I >= 1024 and O % 8 == 0 and _is32(x2):
+        acc = gemm(xa, wa, B_, O, I, lda=lda, ldb=ldb)                    # fp32 split-K accumulation, finished in place
+        L().bias_act_f32(acc.data_ptr(), _p(bias), acc.data_ptr(), int(B_), int(O), int(bool(relu)), _st(x2))
+        return acc
     if FC_SPLITK and B_ <= 128 and I >= 1024 and O % 8 == 0:
         # small-batch FC forward is a weight stream: one m-tile, so the parallelism comes from n-tiles x split-K (fp32
         # reductions into a scratch tile), followed by a tiny bias + ReLU + bf16 pass.  (The fused-epilogue kernel needs
@@ -109,6 +133,14 @@ def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld):
     dev = dy.device
     db = db_out if db_out is not None else torch.empty(C, dtype=torch.float32, device=dev)
     contiguous = (ld == C)
+    if _is32(dy):
+        if relu or not contiguous:
+            dym = torch.empty((R, C), dtype=F32, device=dev)
+            L().relu_bias_bwd2_f32(dy.data_ptr(), _p(y), dym.data_ptr(), db.data_ptr(), 0, int(C), int(R), int(C), int(ld), int(bool(relu)), _st(dy))
+        else:
+            dym = dy
+            L().relu_bias_bwd2_f32(dy.data_ptr(), 0, 0, db.data_ptr(), 0, int(C), int(R), int(C), int(ld), 0, _st(dy))
+        return dym, db
     if relu or not contiguous:
         dym = torch.empty((R, C), dtype=BF16, device=dev)
         L().relu_bias_bwd(dy.data_ptr(), _p(y), dym.data_ptr(), db.data_ptr(), int(R), int(C), int(ld), int(bool(relu)), _st(dy))
@@ -137,7 +169,8 @@ def linear_bias_act_bwd(x, w, y, dy, relu, need_dx, dw_out=None, db_out=None):
     dy = _bf(dy).contiguous()
     B_, I = x2.shape
     O = w.shape[0]
-    if O % 8 or I % 8:
+    al = _al(x2)
+    if O % al or I % al:
         return _linear_bwd_padded(x2, w, y, dy, relu, need_dx, dw_out, db_out)
     dym, db = _mask_and_bias_grad(dy, y, relu, db_out.view(-1) if db_out is not None else None, B_, O, O)
     wb = _bf(w)
@@ -155,13 +188,14 @@ def _linear_bwd_padded(x2, w, y, dy, relu, need_dx, dw_out, db_out):
     O = w.shape[0]
     Op, Ip = (O + 7) // 8 * 8, (I + 7) // 8 * 8
     dev = x2.device
+    dt = x2.dtype
     dyf = dy.float()
     if relu:
         dyf = dyf * (y > 0)
     db = dyf.sum(0)
-    dyp = torch.zeros((B_, Op), dtype=BF16, device=dev); dyp[:, :O] = dyf
-    xp = torch.zeros((B_, Ip), dtype=BF16, device=dev); xp[:, :I] = x2
-    wp = torch.zeros((Op, Ip), dtype=BF16, device=dev); wp[:O, :I] = w
+    dyp = torch.zeros((B_, Op), dtype=dt, device=dev); dyp[:, :O] = dyf
+    xp = torch.zeros((B_, Ip), dtype=dt, device=dev); xp[:, :I] = x2
+    wp = torch.zeros((Op, Ip), dtype=dt, device=dev); wp[:O, :I] = w
     dx = gemm(dyp, wp, B_, Ip, Op, b_mn=True, lda=Op, ldb=Ip)[:, :I].contiguous() if need_dx else None
     dwp = torch.empty((Op, Ip), dtype=torch.float32, device=dev)
     gemm(dyp, xp, Op, Ip, B_, a_mn=True, b_mn=True, out=dwp, lda=Op, ldb=Ip, ldc=Ip)
@@ -181,11 +215,13 @@ def _out_hw(H, W, KH, KW, s, p):
 def _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p):
     N, H, W, Ct = x.shape
     K = KH * KW * Cg
-    if KH == 1 and KW == 1 and s == 1 and p == 0 and c_off == 0 and Cg == Ct and Ct % 8 == 0:
+    al = _al(x)
+    if KH == 1 and KW == 1 and s == 1 and p == 0 and c_off == 0 and Cg == Ct and Ct % al == 0:
         return x.view(N * H * W, Ct), Ct, K                     # 1x1 conv: the activation IS the matrix
     Kp = (K + 7) // 8 * 8
-    col = torch.empty((N * Ho * Wo, Kp), dtype=BF16, device=x.device)
-    L().im2col(x.data_ptr(), col.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+    col = torch.empty((N * Ho * Wo, Kp), dtype=x.dtype, device=x.device)
+    fn = L().im2col_f32 if _is32(x) else L().im2col
+    fn(x.data_ptr(), col.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
     return col, Kp, K
 
 
@@ -195,8 +231,8 @@ def _w2d(w, K, Kp):
     w2 = _bf(w).reshape(O, K)
     if Kp == K and w2.data_ptr() % 16 == 0:
         return w2
-    wp = torch.empty((O, Kp), dtype=BF16, device=w.device)
-    L().pad_rows(w2.data_ptr(), wp.data_ptr(), O, K, K, Kp, _st(w))
+    wp = torch.empty((O, Kp), dtype=w2.dtype, device=w.device)
+    (L().pad_rows_f32 if _is32(w2) else L().pad_rows)(w2.data_ptr(), wp.data_ptr(), O, K, K, Kp, _st(w))
     return wp
 
 
@@ -208,8 +244,9 @@ CONV_MODE = os.environ.get("TMPI_CONV", "implicit")      # implicit: TMA-im2col 
 def _implicit_ok(x, w, c_off, Cg, Ot, o_off):
     """TMA im2col needs 16-byte aligned channel slices; C = 3 (first layer) stays on the explicit path."""
     Ct = x.shape[3]
-    return (CONV_MODE == "implicit" and Cg % 8 == 0 and c_off % 8 == 0 and Ct % 8 == 0 and Ot % 8 == 0 and o_off % 8 == 0
-            and w.shape[0] % 8 == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0)
+    al = _al(x)
+    return (CONV_MODE == "implicit" and Cg % al == 0 and c_off % al == 0 and Ct % al == 0 and Ot % al == 0 and o_off % al == 0
+            and w.shape[0] % al == 0 and w.is_contiguous() and w.data_ptr() % 16 == 0)
 
 
 def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
@@ -220,9 +257,9 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
     wb = _bf(w)
     if _implicit_ok(x, wb, c_off, Cg, Ot, o_off):
         # implicit GEMM: the activation tile is gathered by TMA im2col loads inside the kernel — no col matrix
-        yp = y.data_ptr() + o_off * 2
+        yp = y.data_ptr() + o_off * y.element_size()
         L().conv_fprop(x.data_ptr(), wb.data_ptr(), yp, _p(b), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
-                       Og, Ot, int(bool(relu)), 1, 0, _st(x))
+                       Og, Ot, int(bool(relu)), int(not _is32(x)), 0, _st(x), int(_is32(x)))
         return None
     col, Kp, K = _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)
     w2 = _w2d(w, K, Kp)
@@ -234,7 +271,7 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
 
 def _s2d_geom(H, W, C, KH, KW, stride, pad):
     """Geometry of the space-to-depth rewrite of a strided few-channel conv, or None when it does not apply."""
-    if not (CONV_MODE == "implicit" and C < 8 and stride > 1 and pad == 0):
+    if not (CONV_MODE == "implicit" and C < 8 and C % 4 != 0 and stride > 1 and pad == 0):
         return None
     S = stride
     Hs, Ws = -(-H // S), -(-W // S)
@@ -252,13 +289,18 @@ def _conv_s2d_fwd(x, w, b, relu, g):
     N, H, W, C = x.shape
     O, KH, KW, _ = w.shape
     dev = x.device
-    xs = torch.empty((N, Hs, Ws, Cp), dtype=BF16, device=dev)
-    L().space_to_depth(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
-    ws = torch.empty((O, KHs, KWs, Cp), dtype=BF16, device=dev)
-    L().s2d_filter(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 0, _st(x))
-    y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=dev)
+    f32 = _is32(x)
+    xs = torch.empty((N, Hs, Ws, Cp), dtype=x.dtype, device=dev)
+    ws = torch.empty((O, KHs, KWs, Cp), dtype=x.dtype, device=dev)
+    if f32:
+        L().space_to_depth_f32(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
+        L().s2d_filter_pack_f32(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, _st(x))
+    else:
+        L().space_to_depth(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
+        L().s2d_filter(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 0, _st(x))
+    y = torch.empty((N, Ho, Wo, O), dtype=x.dtype, device=dev)
     L().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), _p(b), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O,
-                   int(bool(relu)), 1, 0, _st(x))
+                   int(bool(relu)), int(not f32), 0, _st(x), int(f32))
     return y, xs
 
 
@@ -273,7 +315,7 @@ def _conv_s2d_bwd(xs, w, y, dy, relu, g, dw_out, db_out, pre_masked=False):
     else:
         dym, db = _mask_and_bias_grad(dy.view(M, O), y.view(M, O), relu, db_out.view(-1) if db_out is not None else None, M, O, O)
     dws = torch.empty((O, KHs, KWs, Cp), dtype=torch.float32, device=dev)
-    L().conv_wgrad(dym.data_ptr(), xs.data_ptr(), dws.data_ptr(), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O, _st(xs))
+    L().conv_wgrad(dym.data_ptr(), xs.data_ptr(), dws.data_ptr(), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O, _st(xs), int(_is32(xs)))
     dw = dw_out if dw_out is not None else torch.empty((O, KH, KW, C), dtype=torch.float32, device=dev)
     L().s2d_filter(dws.data_ptr(), dw.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 1, _st(xs))
     return dw, db
@@ -289,7 +331,7 @@ def conv2d_bias_act(x, w, b, stride=1, pad=0, groups=1, relu=True, return_cols=F
         y, xs = _conv_s2d_fwd(x, w, b, relu, g)
         return (y, [("s2d", xs, g)]) if return_cols else y
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
-    y = torch.empty((N, Ho, Wo, O), dtype=BF16, device=x.device)
+    y = torch.empty((N, Ho, Wo, O), dtype=x.dtype, device=x.device)
     Og = O // groups
     cols = []
     for g in range(groups):
@@ -303,12 +345,14 @@ def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu, return_cols=Fal
     N, H, W, C = x.shape
     Og, KH, KW, Cg = w0.shape
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
-    y = torch.empty((N, Ho, Wo, 2 * Og), dtype=BF16, device=x.device)
+    y = torch.empty((N, Ho, Wo, 2 * Og), dtype=x.dtype, device=x.device)
     wb0, wb1 = _bf(w0), _bf(w1)
+    es, f32 = x.element_size(), _is32(x)
     if GROUP2_FUSED and _implicit_ok(x, wb0, 0, Cg, 2 * Og, 0) and _implicit_ok(x, wb1, Cg, Cg, 2 * Og, Og) and (b0 is None) == (b1 is None):
         # both groups in ONE persistent launch: their tiles fill the 148 SMs together instead of two under-filled waves
-        L().conv_fprop2(x.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), y.data_ptr(), y.data_ptr() + Og * 2, _p(b0), _p(b1), N, H, W, C, 0,
-                        int(Cg), int(Cg), KH, KW, Ho, Wo, int(stride), int(pad), Og, 2 * Og, int(bool(relu)), 1, 0, _st(x))
+        L().conv_fprop2(x.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), y.data_ptr(), y.data_ptr() + Og * es, _p(b0), _p(b1), N, H, W, C, 0,
+                        int(Cg), int(Cg), KH, KW, Ho, Wo, int(stride), int(pad), Og, 2 * Og, int(bool(relu)), int(not f32), 0, _st(x),
+                        int(f32))
         return (y, [None, None]) if return_cols else y
     cols = [_conv_fwd_group(x, w0, b0, y, 0, 0, Cg, stride, pad, relu),
             _conv_fwd_group(x, w1, b1, y, Og, Cg, Cg, stride, pad, relu)]
@@ -335,19 +379,21 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
         # ---- implicit GEMM backward: wgrad gathers im2col(x) by TMA; dgrad (stride 1) is a forward conv of dy with the
         # flipped / transposed filter, written straight into dx's channel slice.
         dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
+        es, f32 = x.element_size(), _is32(x)
         L().conv_wgrad(dym.data_ptr(), x.data_ptr(), dw.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p),
-                       Og, int(ldy), _st(x))
+                       Og, int(ldy), _st(x), int(f32))
         if need_dx:
             if s == 1:
                 # dgrad = forward conv of dy with the mirrored, transposed filter — which the kernel's TMA loads read straight
                 # out of the forward weights (MN-major boxes of the mirrored tap): no flipped copy
-                L().conv_fprop(dym.data_ptr() - dy_coff * 2, wb.data_ptr(), dx.data_ptr() + c_off * 2, 0, N, Ho, Wo, int(ldy), int(dy_coff),
-                               Og, KH, KW, H, W, 1, KH - 1 - int(p), int(Cg), Ct, 0, 1, 1, _st(x))
+                L().conv_fprop(dym.data_ptr() - dy_coff * es, wb.data_ptr(), dx.data_ptr() + c_off * es, 0, N, Ho, Wo, int(ldy), int(dy_coff),
+                               Og, KH, KW, H, W, 1, KH - 1 - int(p), int(Cg), Ct, 0, int(not f32), 1, _st(x), int(f32))
             else:
                 colK = KH * KW * Cg
                 Kp = (colK + 7) // 8 * 8
                 dcol = gemm(dym, _w2d(w, colK, Kp), M, Kp, Og, b_mn=True, lda=ldy, ldb=Kp)
-                L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+                (L().col2im_f32 if f32 else L().col2im)(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo,
+                                                        int(s), int(p), Kp, _st(x))
         return dw, db
     col, Kp, K = col if col is not None else _im2col(x, c_off, Cg, KH, KW, Ho, Wo, s, p)   # forward's matrix is reused
     dw = dw_out if dw_out is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
@@ -360,7 +406,8 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
             gemm(dym, w2, M, Kp, Og, b_mn=True, out=dx.view(M, Ct), lda=ldy, ldb=Kp, ldc=Ct)
         else:
             dcol = gemm(dym, w2, M, Kp, Og, b_mn=True, lda=ldy, ldb=Kp)
-            L().col2im(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo, int(s), int(p), Kp, _st(x))
+            (L().col2im_f32 if _is32(x) else L().col2im)(dcol.data_ptr(), dx.data_ptr(), N, H, W, Ct, int(c_off), int(Cg), KH, KW, Ho, Wo,
+                                                         int(s), int(p), Kp, _st(x))
     return dw, db
 
 
@@ -374,8 +421,8 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
             raise RuntimeError("space-to-depth conv path is for the first layer only (no input gradient)")
         dw, db = _conv_s2d_bwd(cols[0][1], w, y, dy, relu, cols[0][2], dw_out, db_out, pre_masked)
         return None, dw, db
-    if (Cg % 8 or O % 8) and need_dx:
-        raise RuntimeError("conv dgrad needs channel counts that are multiples of 8")
+    if (Cg % _al(x) or O % _al(x)) and need_dx:
+        raise RuntimeError("conv dgrad needs channel counts that are multiples of 16 bytes")
     dx = torch.empty_like(x) if need_dx else None
     Og = O // groups
     if groups == 1:
@@ -408,19 +455,20 @@ def conv2d_group2_bias_act_bwd(x, w0, w1, y, dy, stride, pad, relu, need_dx, out
         dev = x.device
         db0 = outs[1] if outs[1] is not None else torch.empty(Og, dtype=torch.float32, device=dev)
         db1 = outs[3] if outs[3] is not None else torch.empty(Og, dtype=torch.float32, device=dev)
+        es, f32 = x.element_size(), _is32(x)
         if pre_masked:
             dym = dy
         else:
-            dym = torch.empty((M, Ot), dtype=BF16, device=dev)
-            L().relu_bias_bwd2(dy.data_ptr(), y.data_ptr(), dym.data_ptr(), db0.data_ptr(), db1.data_ptr(), int(Og), int(M), int(Ot), int(Ot),
-                               int(bool(relu)), _st(x))
+            dym = torch.empty((M, Ot), dtype=x.dtype, device=dev)
+            (L().relu_bias_bwd2_f32 if f32 else L().relu_bias_bwd2)(dy.data_ptr(), y.data_ptr(), dym.data_ptr(), db0.data_ptr(), db1.data_ptr(),
+                                                                     int(Og), int(M), int(Ot), int(Ot), int(bool(relu)), _st(x))
         dw0 = outs[0] if outs[0] is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
         dw1 = outs[2] if outs[2] is not None else torch.empty((Og, KH, KW, Cg), dtype=torch.float32, device=dev)
-        L().conv_wgrad2(dym.data_ptr(), dym.data_ptr() + Og * 2, x.data_ptr(), dw0.data_ptr(), dw1.data_ptr(), N, H, W, Ct, 0, int(Cg), int(Cg),
-                        KH, KW, Ho, Wo, int(stride), int(pad), Og, int(Ot), _st(x))
+        L().conv_wgrad2(dym.data_ptr(), dym.data_ptr() + Og * es, x.data_ptr(), dw0.data_ptr(), dw1.data_ptr(), N, H, W, Ct, 0, int(Cg), int(Cg),
+                        KH, KW, Ho, Wo, int(stride), int(pad), Og, int(Ot), _st(x), int(f32))
         if need_dx:
-            L().conv_fprop2(dym.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), dx.data_ptr(), dx.data_ptr() + Cg * 2, 0, 0, N, Ho, Wo, int(Ot), 0,
-                            int(Og), int(Og), KH, KW, H, W, 1, KH - 1 - int(pad), int(Cg), Ct, 0, 1, 1, _st(x))
+            L().conv_fprop2(dym.data_ptr(), wb0.data_ptr(), wb1.data_ptr(), dx.data_ptr(), dx.data_ptr() + Cg * es, 0, 0, N, Ho, Wo, int(Ot), 0,
+                            int(Og), int(Og), KH, KW, H, W, 1, KH - 1 - int(pad), int(Cg), Ct, 0, int(not f32), 1, _st(x), int(f32))
         return dx, (dw0, db0, dw1, db1)
     dw0, db0 = _conv_bwd_group(x, w0, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, outs[0], outs[1],
                                col=cols[0] if cols else None, pre_masked=pre_masked)
@@ -434,10 +482,11 @@ def pool2d_fwd(x, ksize, stride, pad, mode):
     x = _bf(x).contiguous()
     N, H, W, C = x.shape
     Ho, Wo = _out_hw(H, W, ksize, ksize, stride, pad)
-    y = torch.empty((N, Ho, Wo, C), dtype=BF16, device=x.device)
+    y = torch.empty((N, Ho, Wo, C), dtype=x.dtype, device=x.device)
     is_max = mode == "max"
     arg = torch.empty((N, Ho, Wo, C), dtype=torch.uint8, device=x.device) if is_max else None
-    L().pool_fwd(x.data_ptr(), y.data_ptr(), _p(arg), N, H, W, C, Ho, Wo, int(ksize), int(stride), int(pad), int(is_max), _st(x))
+    (L().pool_fwd_f32 if _is32(x) else L().pool_fwd)(x.data_ptr(), y.data_ptr(), _p(arg), N, H, W, C, Ho, Wo, int(ksize), int(stride),
+                                                     int(pad), int(is_max), _st(x))
     return y, arg
 
 
@@ -445,9 +494,9 @@ def pool2d_bwd_arg(dy, arg, xshape, ksize, stride, pad, mode):
     dy = _bf(dy).contiguous()
     N, H, W, C = xshape
     Ho, Wo = dy.shape[1], dy.shape[2]
-    dx = torch.empty(tuple(xshape), dtype=BF16, device=dy.device)
-    L().pool_bwd(dy.data_ptr(), _p(arg), dx.data_ptr(), N, H, W, C, Ho, Wo, int(ksize), int(stride), int(pad),
-                 int(mode == "max"), _st(dy))
+    dx = torch.empty(tuple(xshape), dtype=dy.dtype, device=dy.device)
+    (L().pool_bwd_f32 if _is32(dy) else L().pool_bwd)(dy.data_ptr(), _p(arg), dx.data_ptr(), N, H, W, C, Ho, Wo, int(ksize), int(stride),
+                                                      int(pad), int(mode == "max"), _st(dy))
     return dx
 
 
@@ -455,7 +504,8 @@ def lrn(x, n=5, k=2.0, alpha=1e-4, beta=0.75):
     x = _bf(x).contiguous()
     C = x.shape[-1]
     y = torch.empty_like(x)
-    L().lrn_fwd(x.data_ptr(), y.data_ptr(), x.numel() // C, C, int(n), float(k), float(alpha), float(beta), _st(x))
+    (L().lrn_fwd_f32 if _is32(x) else L().lrn_fwd)(x.data_ptr(), y.data_ptr(), x.numel() // C, C, int(n), float(k), float(alpha),
+                                                   float(beta), _st(x))
     return y, None
 
 
@@ -464,7 +514,8 @@ def lrn_bwd(x, dy, n=5, k=2.0, alpha=1e-4, beta=0.75):
     dy = _bf(dy).contiguous()
     C = x.shape[-1]
     dx = torch.empty_like(x)
-    L().lrn_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel() // C, C, int(n), float(k), float(alpha), float(beta), _st(x))
+    (L().lrn_bwd_f32 if _is32(x) else L().lrn_bwd)(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), x.numel() // C, C, int(n), float(k),
+                                                   float(alpha), float(beta), _st(x))
     return dx
 
 
@@ -474,15 +525,15 @@ def dropout_fwd(x, p_drop, layer_id):
     y = torch.empty_like(x)
     mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
     step = step_counter(x.device)
-    L().dropout_fwd(x.data_ptr(), y.data_ptr(), mask.data_ptr(), x.numel(), float(p_drop), int(rng_state()["seed"]),
-                    int(layer_id), step.data_ptr(), _st(x))
+    (L().dropout_fwd_f32 if _is32(x) else L().dropout_fwd)(x.data_ptr(), y.data_ptr(), mask.data_ptr(), x.numel(), float(p_drop),
+                                                           int(rng_state()["seed"]), int(layer_id), step.data_ptr(), _st(x))
     return y, mask
 
 
 def dropout_bwd(dy, mask):
     dy = _bf(dy).contiguous()
     dx = torch.empty_like(dy)
-    L().dropout_bwd(dy.data_ptr(), mask.data_ptr(), dx.data_ptr(), dy.numel(), _st(dy))
+    (L().dropout_bwd_f32 if _is32(dy) else L().dropout_bwd)(dy.data_ptr(), mask.data_ptr(), dx.data_ptr(), dy.numel(), _st(dy))
     return dx
 
 
@@ -494,12 +545,14 @@ def softmax_xent(logits, labels, weight=1.0):
     dl = torch.empty_like(lg)
     rowstat = torch.empty((B_, 3), dtype=torch.float32, device=lg.device)
     out3 = torch.empty(3, dtype=torch.float32, device=lg.device)
-    L().softmax_xent(lg.data_ptr(), labels.data_ptr(), dl.data_ptr(), rowstat.data_ptr(), out3.data_ptr(), B_, C, float(weight), _st(lg))
+    (L().softmax_xent_f32 if _is32(lg) else L().softmax_xent)(lg.data_ptr(), labels.data_ptr(), dl.data_ptr(), rowstat.data_ptr(),
+                                                              out3.data_ptr(), B_, C, float(weight), _st(lg))
     return out3[0], out3[1], out3[2], dl
 
 
 # --------------------------------------------------------------------------- loader kernel
-def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype=BF16, out=None, c_out=None):
+def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype=None, out=None, c_out=None):
+    out_dtype = out_dtype or ADT()
     x = x.contiguous()
     N, H, W, C = x.shape
     ch, cw = crop_hw

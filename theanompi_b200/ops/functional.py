@@ -96,7 +96,9 @@ def linear_bias_act(x, w, b, relu=True):
 # --------------------------------------------------------------------------- conv
 def _fused_pool_ok(x, relu, pool):
     """conv(+ReLU) → max-pool blocks run their backward through ONE fused kernel (pool scatter + ReLU mask + bias grad)."""
-    return pool is not None and x.is_cuda and relu and pool[3] == "max"
+    # (bf16 path only: the fused kernel works on packed bf16 lanes; the fp32 / tf32 path runs pool-backward and ReLU-mask +
+    # bias-gradient as two kernels)
+    return pool is not None and x.is_cuda and relu and pool[3] == "max" and x.dtype == torch.bfloat16
 
 
 def _pool_fwd_after(ctx, impl, y, pool):
@@ -385,7 +387,6 @@ def softmax_xent(logits, labels):
 def crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype=None):
     if x.is_cuda:
         from . import cuda_impl
-        return cuda_impl.crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips,
-                                               out_dtype or torch.bfloat16)
+        return cuda_impl.crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips, out_dtype)
     return ref.crop_mirror_normalize(x, mean, std_scale, crop_hw, offsets, flips,
                                      out_dtype or torch.float32)

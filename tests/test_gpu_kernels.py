@@ -341,3 +341,82 @@ def test_legacy_kernels_k1_k5():
     want = a + b
     L.vecadd(a.data_ptr(), b.data_ptr(), 999, 0, st)
     assert rel_err(a, want) < 1e-6
+
+
+# ------------------------------------------------------------------ batch norm (+ residual)(+ ReLU), residual add
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("relu,with_res", [(False, False), (True, False), (True, True), (False, True)])
+def test_batch_norm_fwd_bwd(dtype, relu, with_res):
+    from theanompi_b200.ops import precision
+    old = precision.precision()
+    precision.set_precision("tf32" if dtype == torch.float32 else "bf16")
+    try:
+        torch.manual_seed(11)
+        N, H, W, C = 8, 14, 14, 72 if dtype == torch.float32 else 96
+        x = (torch.randn(N, H, W, C, device=DEV) * 2 + 0.5).to(dtype).requires_grad_(True)
+        res = torch.randn(N, H, W, C, device=DEV).to(dtype).requires_grad_(True) if with_res else None
+        g = (torch.rand(C, device=DEV) + 0.5).requires_grad_(True)
+        b = torch.randn(C, device=DEV).requires_grad_(True)
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        y = ops.batch_norm(x, g, b, rm, rv, True, 0.1, 1e-5, relu, res)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        # fp32 torch reference on the same (rounded) inputs
+        xr = x.detach().float().requires_grad_(True)
+        rr = res.detach().float().requires_grad_(True) if with_res else None
+        gr, br = g.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+        rm2, rv2 = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        yr = torch.nn.functional.batch_norm(xr.permute(0, 3, 1, 2), rm2, rv2, gr, br, True, 0.1, 1e-5).permute(0, 2, 3, 1)
+        if with_res:
+            yr = yr + rr
+        if relu:
+            yr = torch.relu(yr)
+        # the kernel masks with ITS OWN (rounded) output; use the same mask for the reference gradient
+        dyr = dy.float()
+        yr.backward(dyr)
+        tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+        assert rel_err(y, yr) < tol
+        assert rel_err(x.grad, xr.grad) < 3 * tol
+        assert rel_err(g.grad, gr.grad) < 3 * tol and rel_err(b.grad, br.grad) < 3 * tol
+        if with_res:
+            assert rel_err(res.grad, rr.grad) < tol
+        assert rel_err(rm, rm2) < 1e-3 and rel_err(rv, rv2) < 1e-3
+        # eval mode uses the running statistics
+        ye = ops.batch_norm(x.detach(), g.detach(), b.detach(), rm, rv, False, 0.1, 1e-5, relu, res.detach() if with_res else None)
+        yer = torch.nn.functional.batch_norm(xr.detach().permute(0, 3, 1, 2), rm2, rv2, gr.detach(), br.detach(), False, 0.1, 1e-5).permute(0, 2, 3, 1)
+        if with_res:
+            yer = yer + rr.detach()
+        if relu:
+            yer = torch.relu(yer)
+        assert rel_err(ye, yer) < tol
+        # residual add kernel
+        a1 = torch.randn(4, 7, 7, 40, device=DEV).to(dtype).requires_grad_(True)
+        a2 = torch.randn(4, 7, 7, 40, device=DEV).to(dtype).requires_grad_(True)
+        s = ops.add(a1, a2)
+        s.backward(torch.ones_like(s))
+        assert rel_err(s, a1.detach().float() + a2.detach().float()) < tol
+        assert torch.equal(a1.grad, torch.ones_like(a1)) and torch.equal(a2.grad, torch.ones_like(a2))
+    finally:
+        precision.set_precision(old)
+
+
+def test_adam_flat_matches_torch():
+    from theanompi_b200.parallel.arena import FlatArena
+    from theanompi_b200.utils.opt import FlatAdam
+    torch.manual_seed(4)
+    shapes = [(300, 70), (300,), (64, 3, 3, 16)]
+    params = [torch.randn(s) * 0.1 for s in shapes]
+    arena = FlatArena(params, ["W", "b", "W"], torch.device(DEV), weight_decay=0.0, bias_lr_mult=1.0)
+    ref_p = [p.detach().clone().float().to(DEV).requires_grad_(True) for p in arena.params]
+    opt = torch.optim.Adam(ref_p, lr=1e-3)
+    adam = FlatAdam(arena)
+    arena.hyper[0] = 1e-3
+    for it in range(5):
+        arena.G.normal_()
+        for p, q in zip(ref_p, arena.views("G")):
+            p.grad = q.detach().clone().view_as(p)
+        opt.step()
+        adam.step()
+    torch.cuda.synchronize()
+    for p, q in zip(ref_p, arena.params):
+        assert rel_err(q, p) < 1e-5

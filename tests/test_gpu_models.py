@@ -64,6 +64,48 @@ def test_resnet50_cdd_flat_sgd():
          dict(batch_size=4, file_batch_size=4, blocks=(1, 1, 1, 1), no_paraload=True, **IMNET), steps=2, sync="cdd")
 
 
+def test_torch_adapter_models_still_run():
+    """The torch-module variants (cuDNN / cuBLAS through TorchModelBase) stay available as library yardsticks."""
+    _run("theanompi_b200.models.lasagne_model_zoo.resnet50", "ResNet50Torch",
+         dict(batch_size=4, file_batch_size=4, blocks=(1, 1, 1, 1), no_paraload=True, **IMNET), steps=2, sync="cdd")
+    _run("theanompi_b200.models.keras_model_zoo.wresnet", "Wide_ResNetTorch",
+         dict(batch_size=16, file_batch_size=16, depth=10, widen=2, data_kwargs=dict(n_synthetic=128, synthetic=True)), steps=2)
+
+
+@pytest.mark.parametrize("which", ["resnet", "wrn"])
+def test_native_residual_nets_match_fp32_reference(which):
+    """Native ResNet / Wide-ResNet (tcgen05 convs + fused BatchNormal kernels) vs the SAME model on the plain-torch fp32
+    reference ops (CPU), same weights, same batch: loss of the first steps within bf16 accuracy, no library kernels launched."""
+    import importlib
+    from theanompi_b200.models import layers2
+    from theanompi_b200.ops import native
+    from theanompi_b200.utils.recorder import Recorder
+    if which == "resnet":
+        mod, cls = "theanompi_b200.models.lasagne_model_zoo.resnet50", "ResNet50"
+        cfg = dict(batch_size=8, file_batch_size=8, blocks=(1, 1, 1, 1), no_paraload=True, n_class=16,
+                   data_kwargs=dict(n_train_files=4, n_val_files=1, synthetic=True))
+    else:
+        mod, cls = "theanompi_b200.models.keras_model_zoo.wresnet", "Wide_ResNet"
+        cfg = dict(batch_size=32, file_batch_size=32, depth=10, widen=2, data_kwargs=dict(n_synthetic=256, synthetic=True))
+    losses = {}
+    for dev in ("cpu", "cuda:0"):
+        layers2.reseed(); layers2.Dropout.layers.clear(); layers2.Crop.layers.clear(); layers2.BatchNormal.layers.clear()
+        m = getattr(importlib.import_module(mod), cls)(dict(verbose=False, rank=0, size=1, device=dev, cuda_graph=False, **cfg))
+        m.rand_crop = False
+        m.compile_iter_fns("avg")
+        rec = Recorder(None, 10 ** 6, cls, False, device=dev)
+        native.reset_launch_count()
+        for i in range(3):
+            m.train_iter(i, rec)
+        losses[dev] = [float(c) for c in rec.train_info["cost"]]
+        if dev != "cpu":
+            torch.cuda.synchronize()
+            assert native.launch_count() > 50
+        m.cleanup()
+    for a, b in zip(losses["cpu"], losses["cuda:0"]):
+        assert abs(a - b) < 0.08 * max(1.0, abs(a)), losses
+
+
 def test_wide_resnet_adam():
     _run("theanompi_b200.models.keras_model_zoo.wresnet", "Wide_ResNet",
          dict(batch_size=16, file_batch_size=16, depth=10, widen=2, data_kwargs=dict(n_synthetic=128, synthetic=True)), steps=3)

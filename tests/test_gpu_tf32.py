@@ -138,11 +138,11 @@ def test_layer_kernels_fp32():
     x = torch.randn(4, 13, 13, 64, device=DEV).requires_grad_(True)
     for mode, (k, s, p) in (("max", (3, 2, 0)), ("max", (2, 2, 0)), ("max", (3, 1, 1)), ("avg", (5, 3, 0)), ("avg", (3, 1, 1))):
         y = ops.pool2d(x, k, s, p, mode)
-        xr = x.detach().clone().requires_grad_(True)
+        xr = x.detach().cpu().clone().requires_grad_(True)           # ground truth on the CPU (plain fp32 torch)
         yr = ref.pool2d(xr, k, s, p, mode)
         dy = torch.randn_like(y)
-        y.backward(dy); yr.backward(dy)
-        assert rel_err(y, yr) < 1e-6 and rel_err(x.grad, xr.grad) < 1e-5, (mode, k, s, p)
+        y.backward(dy); yr.backward(dy.cpu())
+        assert rel_err(y.cpu(), yr) < 1e-6 and rel_err(x.grad.cpu(), xr.grad) < 1e-5, (mode, k, s, p)
         x.grad = None
     # LRN
     y = ops.lrn(x, 5, 2.0, 1e-4, 0.75)

@@ -23,6 +23,16 @@ def test_fused_kernels_two_ranks():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("case", ["strategies", "easgd", "gosgd", "barrier"])
+def test_protocols_and_strategies_numeric(case):
+    """Per-strategy numeric checks on GPUs (the reference's test-exchanger suite), EASGD lost-update stress through the
+    device-side ticket lock, GOSGD push-sum conservation under heavy gossip, 10,000-barrier stress with skewed launches."""
+    n = min(4, torch.cuda.device_count()) if case in ("easgd", "gosgd") else 2
+    r = _torchrun(n, "tests/mp_proto_check.py", case, port=29613, timeout=600)
+    assert r.returncode == 0 and "MP_PROTO_CHECK_OK" in r.stdout, r.stdout[-4000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_bench_two_ranks_fused_matches_loss_scale():
     r = _torchrun(2, "bench.py", "--gpus", "2", "--steps", "4", "--warmup", "3", port=29612)
     assert r.returncode == 0 and '"n_gpus": 2' in r.stdout, r.stdout[-4000:]
@@ -44,7 +54,7 @@ def _run_rule(rule_cls, devices, cfg=None, env=None, timeout=240):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
-@pytest.mark.parametrize("strategy", ["fused", "nccl32", "p2p32", "asa32", "copper", "nccl16"])
+@pytest.mark.parametrize("strategy", ["fused", "fused_rs", "nccl32", "p2p32", "asa32", "asa16", "copper", "copper16", "nccl16", "ar"])
 def test_rule_bsp_gpu(tmp_path, monkeypatch, strategy):
     import theanompi_b200 as tm
     monkeypatch.chdir(tmp_path)

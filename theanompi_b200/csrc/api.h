@@ -115,9 +115,18 @@ void pad_rows_f32(const void* src, void* dst, long long rows, int cols, long lon
 void space_to_depth_f32(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st);
 void s2d_filter_pack_f32(const void* src, void* dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, cudaStream_t st);
 
+// ---- bn_kernels.cu: batch norm (+ residual)(+ ReLU) forward / backward, residual add  (f32: fp32 activations, else bf16)
+void bn_forward(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* mean, void* rstd, void* run_mean,
+                void* run_var, void* scratch, long long R, int C, float momentum, float eps, int training, int relu, int f32, cudaStream_t st);
+void bn_backward(const void* x, const void* dy, const void* y, void* dx, void* dres, const void* gamma, const void* mean, const void* rstd,
+                 void* dgamma, void* dbeta, long long R, int C, int relu, int f32, cudaStream_t st);
+void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cudaStream_t st);
+
 // ---- comm_kernels.cu
 void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, float mu,
               int nesterov, float inv_k, long long lo, long long hi, int filter, cudaStream_t st);
+void adam_flat(void* W, const void* G, void* M, void* V, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, void* step,
+               float b1, float b2, float eps, long long lo, long long hi, cudaStream_t st);
 void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStream_t st);
 void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t st);
 void device_barrier(const CommCtx& c, cudaStream_t st);

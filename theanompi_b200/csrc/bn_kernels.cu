@@ -1,0 +1,255 @@
+// Batch normalisation (+ residual add)(+ ReLU) forward / backward and the residual `add`, NHWC, bf16 or fp32 activations, fp32
+// statistics / parameters.  The reference takes these from Lasagne / Keras (lasagne_model_zoo/resnet50.py:14-77 batch_norm +
+// ElemwiseSumLayer + rectify; keras_model_zoo/wresnet.py:37-82 BatchNormalization / merge) and special-cases parameters NAMED
+// gamma / beta in its optimizer and exchanger (lib/opt.py:207-226, lib/exchanger.py:35-43).
+//
+//   forward (training)   stats:    per-channel Σx, Σx² (row slabs per CTA, column sums in registers → smem → one atomic per CTA)
+//                        finalize: mean, rstd, running statistics (momentum update, unbiased variance)
+//                        apply:    y = γ·(x − mean)·rstd + β  [+ residual] [ReLU]
+//   backward             reduce:   g = dy ⊙ [y > 0];  dβ = Σ g,  dγ = Σ g·x̂           (x̂ = (x − mean)·rstd)
+//                        apply:    dx = γ·rstd·(g − dβ/M − x̂·dγ/M);  d residual = g
+// M = N·H·W rows.  Each pass is one streaming kernel over the activation tensor (16-byte vectors).
+#include "common.cuh"
+#include "api.h"
+#include <algorithm>
+
+namespace tmpi {
+
+template <typename T> struct VecIO;
+template <> struct VecIO<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { unpack8(*reinterpret_cast<const bf16x8*>(p), f); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) { *reinterpret_cast<bf16x8*>(p) = pack8(f); }
+};
+template <> struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const float* p, float* f) {
+    const float4 v = *reinterpret_cast<const float4*>(p); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+
+static inline int grid1(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------- column reductions over row slabs
+// MODE 0: a = Σ x, b = Σ x²            (forward statistics)
+// MODE 1: a = Σ g, b = Σ g·x̂          (backward: g = dy ⊙ [y > 0] when relu)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bn_colreduce_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ out_a,
+                                                          float* __restrict__ out_b, long long R, int C, int relu, int VT, int rows_per_cta) {
+  constexpr int N = VecIO<T>::N;
+  extern __shared__ float sm[];                       // [2][RL][VT*N]
+  const int nvec = C / N;
+  const int RL = blockDim.x / VT;
+  const int tv = threadIdx.x % VT, tr = threadIdx.x / VT;
+  const int cv = blockIdx.y * VT + tv;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  float a[N], b[N], mu[N], rs[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) { a[i] = 0.f; b[i] = 0.f; mu[i] = 0.f; rs[i] = 1.f; }
+  const bool on = tr < RL && cv < nvec;
+  if (on) {
+    if (MODE == 1) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) { mu[i] = mean[cv * N + i]; rs[i] = rstd[cv * N + i]; }
+    }
+    const long long rend = min(R, r0 + rows_per_cta);
+    for (long long r = r0 + tr; r < rend; r += RL) {
+      float xv[N];
+      VecIO<T>::ld(x + r * C + cv * N, xv);
+      if (MODE == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] += xv[i]; b[i] += xv[i] * xv[i]; }
+      } else {
+        float g[N];
+        VecIO<T>::ld(dy + r * C + cv * N, g);
+        if (relu) {
+          float yv[N];
+          VecIO<T>::ld(y + r * C + cv * N, yv);
+#pragma unroll
+          for (int i = 0; i < N; ++i) if (!(yv[i] > 0.f)) g[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) { a[i] += g[i]; b[i] += g[i] * (xv[i] - mu[i]) * rs[i]; }
+      }
+    }
+  }
+  float* sa = sm;
+  float* sb = sm + RL * VT * N;
+  if (tr < RL) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) { sa[(tr * VT + tv) * N + i] = a[i]; sb[(tr * VT + tv) * N + i] = b[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < VT * N) {
+    const int v = threadIdx.x / N, i = threadIdx.x % N;
+    const int c = (blockIdx.y * VT + v) * N + i;
+    if (c < C) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int t = 0; t < RL; ++t) { s0 += sa[(t * VT + v) * N + i]; s1 += sb[(t * VT + v) * N + i]; }
+      atomicAdd(out_a + c, s0);
+      atomicAdd(out_b + c, s1);
+    }
+  }
+}
+
+template <typename T, int MODE>
+static void colreduce(const void* x, const void* dy, const void* y, const float* mean, const float* rstd, float* a, float* b, long long R,
+                      int C, int relu, cudaStream_t st) {
+  constexpr int N = VecIO<T>::N;
+  if (C % N) throw std::runtime_error("batch_norm: C must be a multiple of the 16-byte vector width");
+  const int nvec = C / N;
+  const int VT = nvec < 32 ? nvec : 32;
+  const int RL = 256 / VT;
+  // enough CTAs to fill the machine a few times, few enough that the atomics stay cheap
+  long long slabs = std::max<long long>(1, std::min<long long>((R + RL - 1) / RL, (long long)sm_count() * 8 / std::max(1, (nvec + VT - 1) / VT)));
+  const int rows_per_cta = (int)((R + slabs - 1) / slabs);
+  dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
+  const size_t smem = (size_t)2 * RL * VT * N * sizeof(float);
+  check_cuda(cudaMemsetAsync(a, 0, (size_t)C * 4, st), "bn memset");
+  check_cuda(cudaMemsetAsync(b, 0, (size_t)C * 4, st), "bn memset");
+  bn_colreduce_kernel<T, MODE><<<grid, 256, smem, st>>>((const T*)x, (const T*)dy, (const T*)y, mean, rstd, a, b, R, C, relu, VT, rows_per_cta);
+}
+
+// mean / rstd from the sums (training) or from the running statistics (eval); momentum update of the running statistics
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var, int C, float inv_m,
+                                   float unbias, float momentum, float eps, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (training) {
+    const float m = sum[c] * inv_m;
+    const float v = fmaxf(sumsq[c] * inv_m - m * m, 0.f);
+    mean[c] = m;
+    rstd[c] = rsqrtf(v + eps);
+    if (run_mean) {
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * m;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * v * unbias;
+    }
+  } else {
+    mean[c] = run_mean[c];
+    rstd[c] = rsqrtf(run_var[c] + eps);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      const float* __restrict__ mean, const float* __restrict__ rstd, long long total_vec,
+                                                      int nvec, int relu) {
+  constexpr int N = VecIO<T>::N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = (int)(idx % nvec);
+  float xv[N], o[N];
+  VecIO<T>::ld(x + idx * N, xv);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int c = cv * N + i;
+    const float sc = gamma[c] * rstd[c];
+    o[i] = fmaf(xv[i] - mean[c], sc, beta[c]);
+  }
+  if (res) {
+    float rv[N];
+    VecIO<T>::ld(res + idx * N, rv);
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] += rv[i];
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) o[i] = fmaxf(o[i], 0.f);
+  }
+  VecIO<T>::st(y + idx * N, o);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy, const T* __restrict__ y,
+                                                          T* __restrict__ dx, T* __restrict__ dres, const float* __restrict__ gamma,
+                                                          const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                          const float* __restrict__ dgamma, const float* __restrict__ dbeta, long long total_vec,
+                                                          int nvec, int relu, float inv_m) {
+  constexpr int N = VecIO<T>::N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  const int cv = (int)(idx % nvec);
+  float xv[N], g[N], o[N];
+  VecIO<T>::ld(x + idx * N, xv);
+  VecIO<T>::ld(dy + idx * N, g);
+  if (relu) {
+    float yv[N];
+    VecIO<T>::ld(y + idx * N, yv);
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (!(yv[i] > 0.f)) g[i] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const int c = cv * N + i;
+    const float xh = (xv[i] - mean[c]) * rstd[c];
+    o[i] = gamma[c] * rstd[c] * (g[i] - dbeta[c] * inv_m - xh * dgamma[c] * inv_m);
+  }
+  VecIO<T>::st(dx + idx * N, o);
+  if (dres) VecIO<T>::st(dres + idx * N, g);
+}
+
+// y = a + b (the residual merge of pre-activation blocks)
+template <typename T>
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ y, long long total_vec) {
+  constexpr int N = VecIO<T>::N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  float av[N], bv[N];
+  VecIO<T>::ld(a + idx * N, av);
+  VecIO<T>::ld(b + idx * N, bv);
+#pragma unroll
+  for (int i = 0; i < N; ++i) av[i] += bv[i];
+  VecIO<T>::st(y + idx * N, av);
+}
+
+// ---------------------------------------------------------------- launchers (f32 = 1: fp32 activations, else bf16)
+void bn_forward(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* mean, void* rstd, void* run_mean,
+                void* run_var, void* scratch /*2*C floats*/, long long R, int C, float momentum, float eps, int training, int relu, int f32,
+                cudaStream_t st) {
+  float* s0 = (float*)scratch; float* s1 = s0 + C;
+  if (training) {
+    if (f32) colreduce<float, 0>(x, nullptr, nullptr, nullptr, nullptr, s0, s1, R, C, 0, st);
+    else colreduce<__nv_bfloat16, 0>(x, nullptr, nullptr, nullptr, nullptr, s0, s1, R, C, 0, st);
+  }
+  bn_finalize_kernel<<<grid1(C, 256), 256, 0, st>>>(s0, s1, (float*)mean, (float*)rstd, (float*)run_mean, (float*)run_var, C, 1.f / (float)R,
+                                                    R > 1 ? (float)R / (float)(R - 1) : 1.f, momentum, eps, training);
+  const int N = f32 ? 4 : 8;
+  const long long tv = R * (C / N);
+  if (f32) bn_apply_kernel<float><<<grid1(tv, 256), 256, 0, st>>>((const float*)x, (const float*)res, (float*)y, (const float*)gamma, (const float*)beta,
+                                                                  (const float*)mean, (const float*)rstd, tv, C / N, relu);
+  else bn_apply_kernel<__nv_bfloat16><<<grid1(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res, (__nv_bfloat16*)y,
+                                                                      (const float*)gamma, (const float*)beta, (const float*)mean,
+                                                                      (const float*)rstd, tv, C / N, relu);
+  count_launch(training ? 3 : 2); TMPI_CHECK_LAUNCH("bn_forward"); ::tmpi::check_capture(st, "bn_forward");
+}
+
+void bn_backward(const void* x, const void* dy, const void* y, void* dx, void* dres, const void* gamma, const void* mean, const void* rstd,
+                 void* dgamma, void* dbeta, long long R, int C, int relu, int f32, cudaStream_t st) {
+  if (f32) colreduce<float, 1>(x, dy, y, (const float*)mean, (const float*)rstd, (float*)dbeta, (float*)dgamma, R, C, relu, st);
+  else colreduce<__nv_bfloat16, 1>(x, dy, y, (const float*)mean, (const float*)rstd, (float*)dbeta, (float*)dgamma, R, C, relu, st);
+  const int N = f32 ? 4 : 8;
+  const long long tv = R * (C / N);
+  if (f32) bn_bwd_apply_kernel<float><<<grid1(tv, 256), 256, 0, st>>>((const float*)x, (const float*)dy, (const float*)y, (float*)dx, (float*)dres,
+                                                                      (const float*)gamma, (const float*)mean, (const float*)rstd,
+                                                                      (const float*)dgamma, (const float*)dbeta, tv, C / N, relu, 1.f / (float)R);
+  else bn_bwd_apply_kernel<__nv_bfloat16><<<grid1(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)y,
+                                                                          (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, (const float*)gamma,
+                                                                          (const float*)mean, (const float*)rstd, (const float*)dgamma,
+                                                                          (const float*)dbeta, tv, C / N, relu, 1.f / (float)R);
+  count_launch(2); TMPI_CHECK_LAUNCH("bn_backward"); ::tmpi::check_capture(st, "bn_backward");
+}
+
+void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cudaStream_t st) {
+  const int N = f32 ? 4 : 8;
+  if (n % N) throw std::runtime_error("add_tensors: numel must be a multiple of the 16-byte vector width");
+  const long long tv = n / N;
+  if (f32) add_kernel<float><<<grid1(tv, 256), 256, 0, st>>>((const float*)a, (const float*)b, (float*)y, tv);
+  else add_kernel<__nv_bfloat16><<<grid1(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, tv);
+  count_launch(); TMPI_CHECK_LAUNCH("add_tensors"); ::tmpi::check_capture(st, "add_tensors");
+}
+
+}  // namespace tmpi

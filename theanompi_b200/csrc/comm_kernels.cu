@@ -143,6 +143,52 @@ void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group,
   count_launch(); TMPI_CHECK_LAUNCH("sgd_flat"); ::tmpi::check_capture(st, "sgd_flat");
 }
 
+// ============================================================================ flat Adam (Wide-ResNet's optimizer, ref keras_model_zoo/wresnet.py:159)
+// m = b1 m + (1 - b1) g;  v = b2 v + (1 - b2) g^2;  w -= lr * (m / (1 - b1^t)) / (sqrt(v / (1 - b2^t)) + eps), t read from a
+// device counter (the captured CUDA graph keeps counting), lr from device memory, weight decay folded into g, bf16 shadow refreshed.
+__global__ void __launch_bounds__(kThreads) adam_flat_kernel(float* __restrict__ W, const float* __restrict__ G, float* __restrict__ M,
+                                                             float* __restrict__ V, __nv_bfloat16* __restrict__ H,
+                                                             const uint8_t* __restrict__ block_group, GroupTable tab,
+                                                             const float* __restrict__ lr_ptr, const unsigned long long* __restrict__ step,
+                                                             float b1, float b2, float eps, long long blk_lo, long long blk_hi) {
+  const float t = (float)(*step + 1ull);
+  const float c1 = 1.f / (1.f - __powf(b1, t)), c2 = 1.f / (1.f - __powf(b2, t));
+  const float lr0 = *lr_ptr;
+  for (long long b = blk_lo + blockIdx.x; b < blk_hi; b += gridDim.x) {
+    const int g = block_group[b];
+    const float lr = lr0 * tab.lr_mult[g], wd = tab.wd[g];
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    float4 w = *reinterpret_cast<const float4*>(W + i), m = *reinterpret_cast<const float4*>(M + i), v = *reinterpret_cast<const float4*>(V + i);
+    const float4 gg = *reinterpret_cast<const float4*>(G + i);
+#define TMPI_ADAM1(Wc, Mc, Vc, Gc)                                    \
+  {                                                                  \
+    const float ge = Gc + wd * Wc;                                   \
+    Mc = b1 * Mc + (1.f - b1) * ge;                                  \
+    Vc = b2 * Vc + (1.f - b2) * ge * ge;                             \
+    Wc -= lr * (Mc * c1) / (sqrtf(Vc * c2) + eps);                   \
+  }
+    TMPI_ADAM1(w.x, m.x, v.x, gg.x) TMPI_ADAM1(w.y, m.y, v.y, gg.y) TMPI_ADAM1(w.z, m.z, v.z, gg.z) TMPI_ADAM1(w.w, m.w, v.w, gg.w)
+#undef TMPI_ADAM1
+    *reinterpret_cast<float4*>(W + i) = w;
+    *reinterpret_cast<float4*>(M + i) = m;
+    *reinterpret_cast<float4*>(V + i) = v;
+    if (H) *reinterpret_cast<uint2*>(H + i) = pack_bf16x4(w);
+  }
+}
+__global__ void adam_advance_kernel(unsigned long long* step) { if (threadIdx.x == 0 && blockIdx.x == 0) *step += 1ull; }
+
+void adam_flat(void* W, const void* G, void* M, void* V, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, void* step,
+               float b1, float b2, float eps, long long lo, long long hi, cudaStream_t st) {
+  if (lo % kArenaBlock || hi % kArenaBlock) throw std::runtime_error("adam_flat: range must be block aligned");
+  const long long nb = (hi - lo) / kArenaBlock;
+  if (nb <= 0) return;
+  int grid = (int)std::min<long long>(nb, (long long)sm_count() * 8);
+  adam_flat_kernel<<<grid, kThreads, 0, st>>>((float*)W, (const float*)G, (float*)M, (float*)V, (__nv_bfloat16*)H, (const uint8_t*)block_group, tab,
+                                              (const float*)lr_ptr, (const unsigned long long*)step, b1, b2, eps, lo / kArenaBlock, hi / kArenaBlock);
+  adam_advance_kernel<<<1, 32, 0, st>>>((unsigned long long*)step);
+  count_launch(2); TMPI_CHECK_LAUNCH("adam_flat"); ::tmpi::check_capture(st, "adam_flat");
+}
+
 // ============================================================================ fused collectives
 __device__ __forceinline__ void local_block_update(const FusedArgs& a, const Hyper& h, long long b, int g) {
   const long long i = b * kArenaBlock + threadIdx.x * 4;

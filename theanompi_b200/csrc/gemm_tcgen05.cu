@@ -237,13 +237,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms), 1 = SWIZZLE_128B_BASE32B (32-byte atoms: the only layout the tensor
+// core accepts for MN-major 32-bit (tf32) operands — cute::UMMA::Layout_MN_SW128_32B_Atom, TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2u) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address      bits [0,14)
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // leading byte off   bits [16,30)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride byte off    bits [32,46)
   d |= (uint64_t)1 << 46;                                 // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                                 // layout type: SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;                       // layout type
   return d;
 }
 
@@ -458,8 +460,10 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
     constexpr uint32_t kMnStep = (uint32_t)(UMMA_K * 128) >> 4;
     const uint32_t a_lbo = p.a_mn ? (uint32_t)(BK * 128) : 16u, a_step = p.a_mn ? kMnStep : 2u;
     const uint32_t b_lbo = p.b_mn ? (uint32_t)(BK * 128) : 16u, b_step = p.b_mn ? kMnStep : 2u;
-    const uint64_t adesc_base = make_smem_desc(smem_base, a_lbo, 1024u);
-    const uint64_t bdesc_base = make_smem_desc(smem_base + C::A_BYTES, b_lbo, 1024u);
+    // tf32 MN-major: 32-byte swizzle atoms, 4 k-rows (512 B) per atom along K; everything else: 16-byte atoms, 8 rows (1024 B)
+    const uint32_t a_lt = (E::TF32 && p.a_mn) ? 1u : 2u, b_lt = (E::TF32 && p.b_mn) ? 1u : 2u;
+    const uint64_t adesc_base = make_smem_desc(smem_base, a_lbo, a_lt == 1u ? 512u : 1024u, a_lt);
+    const uint64_t bdesc_base = make_smem_desc(smem_base + C::A_BYTES, b_lbo, b_lt == 1u ? 512u : 1024u, b_lt);
     int stage = 0; uint32_t phase = 0;
     int t = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
@@ -695,13 +699,16 @@ static PFN_encodeTiled get_encode() {
 
 // 2-D tensor map (bf16 or fp32 elements): dims {inner, outer}, row pitch in bytes, box {128 bytes, box_outer}, 128B swizzle,
 // zero OOB fill.
-static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer, int esz = 2) {
+static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer, int esz = 2,
+                             int mn_major = 0) {
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand base must be 16B aligned");
   if ((pitch_bytes & 15) != 0) throw std::runtime_error("tmpi_native: TMA operand row pitch must be a multiple of 16 bytes");
-  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int>;
+  using Key = std::tuple<const void*, uint64_t, uint64_t, uint64_t, uint32_t, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{ptr, inner, outer, pitch_bytes, box_outer, esz};
+  Key key{ptr, inner, outer, pitch_bytes, box_outer, esz, mn_major};
+  // MN-major fp32 (tf32) operands must land in the 32-byte-atom swizzle (see make_smem_desc)
+  const CUtensorMapSwizzle swz = (esz == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -711,7 +718,7 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_outer};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
   if (cache.size() > 4096) cache.clear();
@@ -882,10 +889,10 @@ static void gemm_host(const void* A, const void* B, void* C, const float* bias, 
     // split-K accumulates with fp32 atomics: clear the (possibly strided) output first
     check_cuda(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st), "gemm split-K memset");
   }
-  CUtensorMap ta = a_mn ? make_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * ESZ, (uint32_t)BK, ESZ)
-                        : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * ESZ, (uint32_t)BM, ESZ);
-  CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * ESZ, (uint32_t)BK, ESZ)
-                        : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * ESZ, (uint32_t)BN, ESZ);
+  CUtensorMap ta = a_mn ? make_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda * ESZ, (uint32_t)BK, ESZ, 1)
+                        : make_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda * ESZ, (uint32_t)BM, ESZ, 0);
+  CUtensorMap tb = b_mn ? make_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * ESZ, (uint32_t)BK, ESZ, 1)
+                        : make_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * ESZ, (uint32_t)BN, ESZ, 0);
   (void)ATOM;
   if (tall) { if (BN == 128) launch<T, 128, 2>(ta, tb, p, splits, st); else launch<T, 64, 2>(ta, tb, p, splits, st); }
   else if (BN == 128) launch<T, 128, 1>(ta, tb, p, splits, st);
@@ -924,13 +931,14 @@ static PFN_encodeIm2col get_encode_im2col() {
 // box = pixels x 128 bytes of channels (64 bf16 / 32 fp32), 128 B swizzle, zero fill for padding / out-of-range pixels /
 // channels >= Cg.
 static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int S, int P, int pixels,
-                                   int esz) {
+                                   int esz, int mn_major) {
   const char* base = reinterpret_cast<const char*>(x) + (size_t)c_off * esz;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((Ctot * esz) % 16) != 0) throw std::runtime_error("tmpi_native: im2col operand must be 16B aligned");
-  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int, int, int, int>;
+  using Key = std::tuple<const void*, int, int, int, int, int, int, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{base, N, H, W, Ctot, Cg, KH, KW, S, P, pixels, esz};
+  Key key{base, N, H, W, Ctot, Cg, KH, KW, S, P, pixels, esz, mn_major};
+  const CUtensorMapSwizzle swz = (esz == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -942,7 +950,7 @@ static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot,
   cuuint32_t estr[4] = {1u, (cuuint32_t)S, (cuuint32_t)S, 1u};
   CUresult r = get_encode_im2col()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base),
                                    dims, strides, lower, upper, (cuuint32_t)(128 / esz), (cuuint32_t)pixels, estr,
-                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeIm2col failed, code " + std::to_string((int)r));
   if (cache.size() > 4096) cache.clear();
@@ -951,12 +959,13 @@ static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot,
 }
 
 // weights [O][KH*KW][Cg] (contiguous) as a 3-D tiled map, box {box_c ch, 1 tap, box_o out-channels}
-static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o, int box_c, int esz) {
+static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int box_o, int box_c, int esz, int mn_major) {
   if ((reinterpret_cast<uintptr_t>(w) & 15) != 0 || ((Cg * esz) % 16) != 0) throw std::runtime_error("tmpi_native: conv weights must be 16B aligned, C * esz % 16 == 0");
-  using Key = std::tuple<const void*, int, int, int, int, int, int>;
+  using Key = std::tuple<const void*, int, int, int, int, int, int, int>;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
-  Key key{w, O, taps, Cg, box_o, box_c, esz};
+  Key key{w, O, taps, Cg, box_o, box_c, esz, mn_major};
+  const CUtensorMapSwizzle swz = (esz == 4 && mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
   std::lock_guard<std::mutex> lk(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
@@ -966,7 +975,7 @@ static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int b
   cuuint32_t box[3] = {(cuuint32_t)box_c, 1u, (cuuint32_t)box_o};
   cuuint32_t estr[3] = {1u, 1u, 1u};
   CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides,
-                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled(3D weights) failed, code " + std::to_string((int)r));
   if (cache.size() > 4096) cache.clear();
@@ -1004,8 +1013,8 @@ static void conv_fprop_groups(int ngroups, const void* x, const int* c_off, cons
   p.num_kb = KH * KW * p.c_chunks; p.kb_per_split = p.num_kb;
   CUtensorMap ta[2], tb[2];
   for (int g = 0; g < ngroups; ++g) {
-    ta[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BM, ESZ);
-    tb[g] = dgrad ? make_weight_map(w[g], Cg, KH * KW, O, BK, ATOM, ESZ) : make_weight_map(w[g], O, KH * KW, Cg, BN, BK, ESZ);
+    ta[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BM, ESZ, 0);                     // K-major (channels = K)
+    tb[g] = dgrad ? make_weight_map(w[g], Cg, KH * KW, O, BK, ATOM, ESZ, 1) : make_weight_map(w[g], O, KH * KW, Cg, BN, BK, ESZ, 0);
   }
   const CUtensorMap* a1 = ngroups > 1 ? &ta[1] : nullptr;
   const CUtensorMap* b1 = ngroups > 1 ? &tb[1] : nullptr;
@@ -1041,8 +1050,8 @@ static void conv_wgrad_groups(int ngroups, const void* const* dy, const void* x,
   CUtensorMap ta[2], tb[2];
   for (int g = 0; g < ngroups; ++g) {
     if (splits > 1) check_cuda(cudaMemsetAsync(dw[g], 0, (size_t)O * KH * KW * Cg * 4, st), "conv_wgrad memset");
-    ta[g] = make_tmap(dy[g], (uint64_t)O, (uint64_t)M, (uint64_t)ldy * ESZ, (uint32_t)BK, ESZ);
-    tb[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BK, ESZ);
+    ta[g] = make_tmap(dy[g], (uint64_t)O, (uint64_t)M, (uint64_t)ldy * ESZ, (uint32_t)BK, ESZ, 1);          // both operands MN-major
+    tb[g] = make_im2col_map(x, N, H, W, Ctot, c_off[g], Cg, KH, KW, S, P, BK, ESZ, 1);
   }
   launch<T, 128, 1>(ta[0], tb[0], p, splits, st, ngroups > 1 ? &ta[1] : nullptr, ngroups > 1 ? &tb[1] : nullptr);
 }

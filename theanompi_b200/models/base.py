@@ -30,7 +30,7 @@ from .. import ops
 from ..parallel.arena import FlatArena
 from ..utils import nvtx
 from ..utils.opt import FlatSGD, SharedScalar, pre_model_iter_fn
-from .layers2 import Crop, Dropout, count_params
+from .layers2 import BatchNormal, Crop, Dropout, count_params
 
 
 def pick_device(config):
@@ -60,6 +60,7 @@ class ModelBase(object):
     batch_crop_mirror = False
     rand_crop = True
     monitor_grad = False
+    bias_lr_mult = 2.0             # biases train with 2x lr in the reference's optimizer (lib/opt.py:181-268)
     graph_safe = True              # False: the step draws host-side randomness / has host control flow → never auto-capture
     name = "Model"
 
@@ -122,7 +123,7 @@ class ModelBase(object):
         self.params, self.weight_types = list(params), list(weight_types)
         count_params(self.params, verbose=False)
         allocator = self.config.get("arena_allocator")
-        self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta,
+        self.arena = FlatArena(self.params, self.weight_types, self.device, weight_decay=self.eta, bias_lr_mult=self.bias_lr_mult,
                                with_recv=allocator is not None, allocator=allocator,
                                shadow=False if self.precision == "tf32" else self.config.get("_arena_shadow"))
         self.shared_lr = SharedScalar(self.arena.hyper, 0, self.base_lr)
@@ -281,9 +282,9 @@ class ModelBase(object):
     def compile_inference(self):
         def inf_fn(x):
             with torch.no_grad():
-                Dropout.SetDropoutOff(); Crop.SetRandCropOff()
+                Dropout.SetDropoutOff(); Crop.SetRandCropOff(); BatchNormal.SetTrainOff()
                 out = torch.softmax(self.forward(x).float(), dim=1)
-                Dropout.SetDropoutOn(); Crop.SetRandCropOn()
+                Dropout.SetDropoutOn(); Crop.SetRandCropOn(); BatchNormal.SetTrainOn()
             return out
         self.inf_fn = inf_fn
 
@@ -378,9 +379,9 @@ class ModelBase(object):
         if self.subb_v == 0:
             self.last_one_v = self._load_file_batch("val", self.current_v, img, labels,
                                                     self.data.n_batch_val)
-        Dropout.SetDropoutOff(); Crop.SetRandCropOff()
+        Dropout.SetDropoutOff(); Crop.SetRandCropOff(); BatchNormal.SetTrainOff()
         cost, error, error_top5 = self.val_iter_fn(self.subb_v)
-        Dropout.SetDropoutOn(); Crop.SetRandCropOn()
+        Dropout.SetDropoutOn(); Crop.SetRandCropOn(); BatchNormal.SetTrainOn()
         recorder.val_error(count, cost, error, error_top5)
         if (self.subb_v + 1) // self.n_subb == 1:
             self.current_v = 0 if self.last_one_v else self.current_v + 1
@@ -406,6 +407,19 @@ class ModelBase(object):
         """L2 grad-norm monitor (ref ``alex_net.py:311-320``): (sum, max) of log10 norms."""
         norms = torch.stack([g.float().norm() for g in self.arena.views("G")]).clamp_min(1e-30).log10()
         return [float(norms.sum()), float(norms.max())]
+
+    # ------------------------------------------------------------------ checkpoint extras (non-parameter state)
+    def _bn_layers(self):
+        return [l for l in (getattr(self, "layers", None) or []) if isinstance(l, BatchNormal)]
+
+    def extra_state(self):
+        """Batch-norm running statistics (not parameters, so not in the arena)."""
+        return {"bn": [(l.running_mean.detach().cpu(), l.running_var.detach().cpu()) for l in self._bn_layers()]}
+
+    def load_extra_state(self, sd):
+        for l, (m, v) in zip(self._bn_layers(), sd.get("bn", [])):
+            l.running_mean = m.to(self.device).clone()
+            l.running_var = v.to(self.device).clone()
 
     def cleanup(self):
         if getattr(self.data, "para_load", False) and hasattr(self.data, "para_load_close"):

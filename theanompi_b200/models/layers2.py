@@ -264,15 +264,19 @@ class Conv(Layer):
         if W is None:
             assert filter_shape is not None
             W = Normal(_ohwi_from_ref(filter_shape), mean=0, std=0.01)
-        if b is None:
+        if b is False:                                   # bias-free convolution (a BatchNormal follows)
+            b = None
+        elif b is None:
             b = Constant((W.shape[0],), val=0.0)
         elif np.isscalar(b):
             b = Constant((W.shape[0],), val=b)
         self.W, self.b = W, b
         _tag(self.W.val, "W", "W")
-        _tag(self.b.val, "b", "b")
-        self.params = [self.W.val, self.b.val]
-        self.weight_type = ["W", "b"]
+        self.params, self.weight_type = [self.W.val], ["W"]
+        if b is not None:
+            _tag(self.b.val, "b", "b")
+            self.params.append(self.b.val)
+            self.weight_type.append("b")
         self.output_shape = tuple(output_shape) if output_shape else self.get_output_shape(self.input_shape)
         self.name = "Conv (%s)" % lib_conv
         if printinfo:
@@ -285,7 +289,7 @@ class Conv(Layer):
                 _conv_out(W_, kw, self.convstride, self.padsize), O)
 
     def forward(self, x):
-        return ops.conv2d_bias_act(x, self.W.val, self.b.val, self.convstride, self.padsize,
+        return ops.conv2d_bias_act(x, self.W.val, None if self.b is None else self.b.val, self.convstride, self.padsize,
                                    self.group, self.relu)
 
 
@@ -410,39 +414,50 @@ class ConvPoolLRN_bc01(ConvPoolLRN):
 
 
 class BatchNormal(Layer):
-    """Batch normalisation with ``gamma``/``beta`` parameters.  The reference's
-    class is an empty stub (``layers2.py:748-751``) but its optimizer and
-    exchanger special-case params *named* gamma/beta (``opt.py:207-226``,
-    ``exchanger.py:35-43``); this real layer makes those paths exercisable."""
+    """Batch normalisation with ``gamma`` / ``beta`` parameters, optionally fused with a residual add and a ReLU
+    (``forward(x, residual=None)``) — hand-written forward / backward kernels (``csrc/bn_kernels.cu``).
 
-    def __init__(self, input, input_shape=None, eps=1e-5, momentum=0.1, printinfo=True):
+    The reference's class is an empty stub (``layers2.py:748-751``) while its optimizer and exchanger special-case
+    parameters *named* gamma / beta (``opt.py:207-226``, ``exchanger.py:35-43``) and its ResNet50 / Wide-ResNet take
+    batch norm from Lasagne / Keras; this layer is what those models are built from here.  Gradients of gamma / beta are
+    written straight into the arena's G views; train / eval mode is a global switch like ``Dropout``'s."""
+
+    layers = []
+
+    def __init__(self, input, input_shape=None, eps=1e-5, momentum=0.1, relu=False, gamma=1.0, printinfo=True):
         super().__init__()
         self.get_input_shape(input, input_shape)
         C = self.input_shape[-1]
-        self.gamma, self.beta = Constant((C,), 1.0), Constant((C,), 0.0)
+        self.gamma, self.beta = Constant((C,), float(gamma)), Constant((C,), 0.0)
         _tag(self.gamma.val, "gamma", "b"); _tag(self.beta.val, "beta", "b")
         self.params = [self.gamma.val, self.beta.val]
         self.weight_type = ["b", "b"]
         self.running_mean = torch.zeros(C)
         self.running_var = torch.ones(C)
-        self.eps, self.momentum = eps, momentum
+        self.eps, self.momentum, self.relu = eps, momentum, relu
         self.training = True
+        BatchNormal.layers.append(self)
         self.output_shape = self.input_shape
         self.name = "BatchNorm"
         if printinfo:
             self.print_shape()
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
         if self.running_mean.device != x.device:
             self.running_mean = self.running_mean.to(x.device)
             self.running_var = self.running_var.to(x.device)
-        xf = x.float()
-        red = tuple(range(x.dim() - 1))
-        y = torch.nn.functional.batch_norm(
-            xf.movedim(-1, 1), self.running_mean, self.running_var, self.gamma.val, self.beta.val,
-            self.training, self.momentum, self.eps).movedim(1, -1)
-        del red
-        return y.to(x.dtype)
+        return ops.batch_norm(x, self.gamma.val, self.beta.val, self.running_mean, self.running_var, self.training,
+                              self.momentum, self.eps, self.relu, residual)
+
+    @staticmethod
+    def SetTrainOn():
+        for l in BatchNormal.layers:
+            l.training = True
+
+    @staticmethod
+    def SetTrainOff():
+        for l in BatchNormal.layers:
+            l.training = False
 
 
 # =========================================================================== shape layers

@@ -128,9 +128,11 @@ def linear_bias_act(x, w, b, relu=True):
     return gemm(xa, wa, B_, O, I, bias=bias, bias_mode=1 if b is not None else 0, relu=relu, lda=lda, ldb=ldb)
 
 
-def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld):
+def _mask_and_bias_grad(dy, y, relu, db_out, R, C, ld, need_db=True):
     """dym = dy ⊙ (y > 0) (contiguous [R, C]) and db = Σ_rows dym in one pass."""
     dev = dy.device
+    if not need_db and not relu and ld == C:
+        return dy, None                                    # bias-free linear conv (a BatchNormal follows): nothing to do
     db = db_out if db_out is not None else torch.empty(C, dtype=torch.float32, device=dev)
     contiguous = (ld == C)
     if _is32(dy):
@@ -359,7 +361,7 @@ def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride, pad, relu, return_cols=Fal
     return (y, cols) if return_cols else y
 
 
-def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out, col=None, pre_masked=False):
+def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_out, db_out, col=None, pre_masked=False, need_db=True):
     N, H, W, Ct = x.shape
     Og, KH, KW, _ = w.shape
     Ho, Wo, Ot = y.shape[1], y.shape[2], y.shape[3]
@@ -372,7 +374,7 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
         # group's channel slice of the full tensor in place (row pitch Ot)
         dym, db, ldy, dy_coff = dyv, db_out, Ot, o_off
     else:
-        dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot)
+        dym, db = _mask_and_bias_grad(dyv, yv, relu, db_out.view(-1) if db_out is not None else None, M, Og, Ot, need_db)
         ldy, dy_coff = Og, 0
     wb = _bf(w)
     if col is None and _implicit_ok(x, wb, c_off, Cg, Ot, o_off):
@@ -411,7 +413,8 @@ def _conv_bwd_group(x, w, y, dy, dx, o_off, c_off, Cg, s, p, relu, need_dx, dw_o
     return dw, db
 
 
-def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None, cols=None, pre_masked=False):
+def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=None, db_out=None, cols=None, pre_masked=False,
+                        need_db=True):
     x = _bf(x).contiguous()
     dy = _bf(dy).contiguous()
     N, H, W, C = x.shape
@@ -427,7 +430,7 @@ def conv2d_bias_act_bwd(x, w, y, dy, stride, pad, groups, relu, need_dx, dw_out=
     Og = O // groups
     if groups == 1:
         dw, db = _conv_bwd_group(x, w, y, dy, dx, 0, 0, Cg, stride, pad, relu, need_dx, dw_out, db_out,
-                                 col=cols[0] if cols else None, pre_masked=pre_masked)
+                                 col=cols[0] if cols else None, pre_masked=pre_masked, need_db=need_db)
         return dx, dw, db
     dw = dw_out if dw_out is not None else torch.empty(tuple(w.shape), dtype=torch.float32, device=x.device)
     db = db_out if db_out is not None else torch.empty(O, dtype=torch.float32, device=x.device)
@@ -548,6 +551,55 @@ def softmax_xent(logits, labels, weight=1.0):
     (L().softmax_xent_f32 if _is32(lg) else L().softmax_xent)(lg.data_ptr(), labels.data_ptr(), dl.data_ptr(), rowstat.data_ptr(),
                                                               out3.data_ptr(), B_, C, float(weight), _st(lg))
     return out3[0], out3[1], out3[2], dl
+
+
+# --------------------------------------------------------------------------- batch norm (+ residual)(+ ReLU), residual add
+def batch_norm_fwd(x, gamma, beta, run_mean, run_var, training, momentum, eps, relu, res=None):
+    x = _bf(x).contiguous()
+    C = x.shape[-1]
+    R = x.numel() // C
+    dev = x.device
+    y = torch.empty_like(x)
+    mean = torch.empty(C, dtype=F32, device=dev)
+    rstd = torch.empty(C, dtype=F32, device=dev)
+    scratch = torch.empty(2 * C, dtype=F32, device=dev)
+    if res is not None:
+        res = _bf(res).contiguous()
+        assert res.shape == x.shape
+    assert gamma.dtype == F32 and beta.dtype == F32
+    if not training:
+        assert run_mean is not None and run_var is not None
+    L().bn_forward(x.data_ptr(), _p(res), y.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                   _p(run_mean), _p(run_var), scratch.data_ptr(), int(R), int(C), float(momentum), float(eps), int(bool(training)),
+                   int(bool(relu)), int(_is32(x)), _st(x))
+    return y, mean, rstd
+
+
+def batch_norm_bwd(x, dy, y, gamma, mean, rstd, relu, need_dres, dgamma_out=None, dbeta_out=None):
+    x = _bf(x).contiguous()
+    dy = _bf(dy).contiguous()
+    C = x.shape[-1]
+    R = x.numel() // C
+    dev = x.device
+    dx = torch.empty_like(x)
+    # without a ReLU the residual branch receives dy itself: nothing to write
+    dres = torch.empty_like(x) if (need_dres and relu) else None
+    dgamma = dgamma_out.view(-1) if dgamma_out is not None else torch.empty(C, dtype=F32, device=dev)
+    dbeta = dbeta_out.view(-1) if dbeta_out is not None else torch.empty(C, dtype=F32, device=dev)
+    L().bn_backward(x.data_ptr(), dy.data_ptr(), _p(y) if relu else 0, dx.data_ptr(), _p(dres), gamma.data_ptr(), mean.data_ptr(),
+                    rstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(R), int(C), int(bool(relu)), int(_is32(x)), _st(x))
+    if need_dres and not relu:
+        dres = dy
+    return dx, dres, dgamma, dbeta
+
+
+def add(a, b):
+    a = _bf(a).contiguous()
+    b = _bf(b).contiguous()
+    assert a.shape == b.shape
+    y = torch.empty_like(a)
+    L().add_tensors(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), int(_is32(a)), _st(a))
+    return y
 
 
 # --------------------------------------------------------------------------- loader kernel

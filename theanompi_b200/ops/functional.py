@@ -40,6 +40,8 @@ def compute_weight(p):
 
 def _sink(p, grad):
     """Deliver a parameter gradient. Returns what autograd should see."""
+    if p is None or grad is None and getattr(p, "gbuf", None) is None:
+        return None
     gbuf = getattr(p, "gbuf", None)
     if gbuf is None:
         return grad.to(p.dtype).view_as(p)
@@ -161,7 +163,8 @@ class _ConvFn(torch.autograd.Function):
                 else:
                     dy = impl.pool2d_bwd_arg(dy, ctx.saved_tensors[2] if ctx.has_arg else None, tuple(y.shape), *pool)
             dx, dw, db = impl.conv2d_bias_act_bwd(x, wc, y, dy, stride, pad, groups, relu, need_dx,
-                                                  dw_out=_gout(w), db_out=db_out, cols=ctx.cols, pre_masked=pre)
+                                                  dw_out=_gout(w), db_out=db_out, cols=ctx.cols, pre_masked=pre,
+                                                  need_db=b is not None)
             ctx.cols = None
         gb = _sink(b, db)
         gw = _sink(w, dw)
@@ -255,6 +258,60 @@ class _ConvG2Fn(torch.autograd.Function):
 
 def conv2d_group2_bias_act(x, w0, b0, w1, b1, stride=1, pad=0, relu=True, pool=None):
     return _ConvG2Fn.apply(x, w0, b0, w1, b1, stride, pad, relu, pool)
+
+
+# --------------------------------------------------------------------------- batch norm (+ residual)(+ ReLU)
+class _BatchNormFn(torch.autograd.Function):
+    """``relu(γ·x̂ + β + residual)`` as one forward pass (statistics + apply) and one backward pass (reduce + apply); the
+    parameter gradients are written straight into the arena's G views (``_gout`` / ``_sink``).  Reference: Lasagne
+    ``batch_norm`` + ``ElemwiseSumLayer`` + ``rectify`` (``lasagne_model_zoo/resnet50.py:14-77``)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, run_mean, run_var, training, momentum, eps, relu):
+        impl = _impl(x)
+        y, mean, rstd = impl.batch_norm_fwd(x, gamma.detach(), beta.detach(), run_mean, run_var, training, momentum, eps, relu, residual)
+        ctx.gamma, ctx.beta = gamma, beta
+        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.save_for_backward(x, y if relu else x.new_empty(0), mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, rstd = ctx.saved_tensors
+        gamma, beta = ctx.gamma, ctx.beta
+        impl = _impl(x)
+        need_dres = ctx.has_res and ctx.needs_input_grad[3]
+        if impl is ref:
+            dx, dres, dg, db = ref.batch_norm_bwd(x, dy, y, gamma.detach(), mean, rstd, ctx.relu, need_dres)
+        else:
+            dx, dres, dg, db = impl.batch_norm_bwd(x, dy, y, gamma.detach(), mean, rstd, ctx.relu, need_dres,
+                                                   dgamma_out=_gout(gamma), dbeta_out=_gout(beta))
+        gb = _sink(beta, db)
+        gg = _sink(gamma, dg)
+        return dx, gg, gb, dres, None, None, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, run_mean=None, run_var=None, training=True, momentum=0.1, eps=1e-5, relu=False, residual=None):
+    """Batch normalisation over all but the channel (last) axis, optionally fused with a residual add and a ReLU."""
+    return _BatchNormFn.apply(x, gamma, beta, residual, run_mean, run_var, training, momentum, eps, relu)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        if a.is_cuda:
+            from . import cuda_impl
+            return cuda_impl.add(a, b)
+        return a + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    """Residual merge ``a + b`` (native kernel on CUDA; the gradient passes to both branches unchanged)."""
+    return _AddFn.apply(a, b)
 
 
 # --------------------------------------------------------------------------- pool

@@ -198,3 +198,45 @@ def crop_mirror_normalize(x_u8, mean, std_scale, crop_hw, offsets, flips, out_dt
             patch = patch.flip(1)
         out[i] = patch
     return out.to(out_dtype)
+
+
+# --------------------------------------------------------------------------- batch norm (+ residual)(+ ReLU), NHWC
+def batch_norm_fwd(x, gamma, beta, run_mean, run_var, training, momentum, eps, relu, res=None):
+    """y = γ·(x − mean)·rstd + β [+ res] [ReLU]; statistics over all but the last (channel) axis.  Updates the running
+    statistics in place (momentum form, unbiased variance) when training.  Returns (y, mean, rstd)."""
+    xf = x.float()
+    C = x.shape[-1]
+    x2 = xf.reshape(-1, C)
+    R = x2.shape[0]
+    if training:
+        mean = x2.mean(0)
+        var = (x2 * x2).mean(0) - mean * mean
+        var = var.clamp_min(0)
+        if run_mean is not None:
+            with torch.no_grad():
+                run_mean.mul_(1 - momentum).add_(momentum * mean)
+                run_var.mul_(1 - momentum).add_(momentum * var * (R / max(1, R - 1)))
+    else:
+        mean, var = run_mean.float(), run_var.float()
+    rstd = torch.rsqrt(var + eps)
+    y = (xf - mean) * (rstd * gamma.float()) + beta.float()
+    if res is not None:
+        y = y + res.float()
+    if relu:
+        y = torch.relu(y)
+    return y.to(x.dtype), mean, rstd
+
+
+def batch_norm_bwd(x, dy, y, gamma, mean, rstd, relu, need_dres):
+    """Returns (dx, dres, dgamma, dbeta) for :func:`batch_norm_fwd` in training mode."""
+    C = x.shape[-1]
+    g = dy.float()
+    if relu:
+        g = g * (y.float() > 0)
+    xh = (x.float() - mean) * rstd
+    g2, xh2 = g.reshape(-1, C), xh.reshape(-1, C)
+    R = g2.shape[0]
+    dbeta = g2.sum(0)
+    dgamma = (g2 * xh2).sum(0)
+    dx = (gamma.float() * rstd) * (g - dbeta / R - xh * (dgamma / R))
+    return dx.to(x.dtype), (g.to(x.dtype) if need_dres else None), dgamma, dbeta

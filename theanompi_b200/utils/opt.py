@@ -99,6 +99,43 @@ class FlatSGD(object):
             a.H[sl].copy_(w)
 
 
+class FlatAdam(object):
+    """Adam over the whole arena in one native kernel (``csrc/comm_kernels.cu: adam_flat_kernel``): first moment in the arena's
+    U region, second moment in an extra flat buffer, step counter and lr in device memory — the step is CUDA-graph capturable.
+    The reference's Wide-ResNet uses Keras Adam (``keras_model_zoo/wresnet.py:159``)."""
+
+    def __init__(self, arena, b1=0.9, b2=0.999, eps=1e-8):
+        self.arena, self.b1, self.b2, self.eps = arena, b1, b2, eps
+        self.V = torch.zeros_like(arena.W)
+        self.t = torch.zeros(1, dtype=torch.int64, device=arena.W.device)
+
+    def step(self, lr=None):
+        a = self.arena
+        nat = _native_for(a.W)
+        if nat is not None:
+            from ..ops.cuda_impl import L, _table, _p, _st
+            lrm, wd, ex = _table(a)
+            L().adam_flat(a.W.data_ptr(), a.G.data_ptr(), a.U.data_ptr(), self.V.data_ptr(), _p(a.H), a.block_group.data_ptr(), lrm, wd, ex,
+                          a.hyper.data_ptr(), self.t.data_ptr(), float(self.b1), float(self.b2), float(self.eps), 0, int(a.numel), _st(a.W))
+            return
+        lr = float(a.hyper[0]) if lr is None else lr
+        self.t += 1
+        t = float(self.t)
+        g = a.G + a.wd_vector() * a.W
+        a.U.mul_(self.b1).add_(g, alpha=1 - self.b1)
+        self.V.mul_(self.b2).addcmul_(g, g, value=1 - self.b2)
+        mh, vh = a.U / (1 - self.b1 ** t), self.V / (1 - self.b2 ** t)
+        a.W.sub_(lr * a.lr_mult_vector() * mh / (vh.sqrt() + self.eps))
+        if a.H is not None:
+            a.H.copy_(a.W)
+
+    def state_dict(self):
+        return {"V": self.V.detach().cpu(), "t": int(self.t)}
+
+    def load_state_dict(self, sd):
+        self.V.copy_(sd["V"].to(self.V.device)); self.t.fill_(int(sd["t"]))
+
+
 # --------------------------------------------------------------------------- classic split (API parity)
 def _ex(a):
     return a.exch_vector()

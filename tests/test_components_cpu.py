@@ -294,6 +294,32 @@ def test_loader_handoff_identity_cpu():
     ld.drain(); d.para_load_close()
 
 
+def test_loader_process_mode_cpu(tmp_path):
+    """``TMPI_LOADER=process``: a separate loader process fills the shared-memory ring from real .npy batch files; what the
+    trainer reads equals normalise+crop of the files (ref proc_load_mpi.py:16-133, test-paraload-cnmem)."""
+    from theanompi_b200.models.data.loader import ParaLoader
+    from theanompi_b200.models.data.proc_loader import ProcReader
+    arrs = []
+    for i in range(3):
+        a = np.random.RandomState(i).randint(0, 256, (4, 32, 32, 3), dtype=np.uint8)
+        np.save(str(tmp_path / ("b%d.npy" % i)), a)
+        arrs.append(a)
+    pr = ProcReader((4, 32, 32, 3), depth=2, pin=False)
+    ld = ParaLoader(pr.read, "cpu", (4, 32, 32, 3), (24, 24), mean=np.full((32, 32, 3), 127.5, np.float32), std_scale=1 / 255.0,
+                    depth=2, rand_crop=False, host_buffers=pr.tensors, on_close=pr.close)
+    try:
+        for i in range(3):
+            ld.request(str(tmp_path / ("b%d.npy" % i)), "val")
+            b = ld.get()
+            want = ((arrs[i].astype(np.float32) - 127.5) / 255.0)[:, 4:28, 4:28, :]
+            assert np.allclose(b.x.numpy(), want, atol=1e-6), i
+        with pytest.raises(RuntimeError):
+            ld.request(str(tmp_path / "missing.npy"), "val")
+    finally:
+        ld.close()
+    assert pr.proc.poll() is not None                    # child gone
+
+
 def test_gemm_wave_planning_host_side():
     """The launcher's wave arithmetic (host code of the native extension, no GPU needed): split-K factors must not spill a
     few tiles into an extra wave, and 256-row tiles are only chosen when they do not waste most of a wave."""

@@ -132,3 +132,30 @@ def test_loader_pipeline_matches_reference_crop():
     want = ((raw.astype(np.float32) - 127.5) / 255.0 / np.array([0.229, 0.224, 0.225], np.float32))[:, 8:56, 8:56, :]
     assert np.abs(b.x.float().cpu().numpy() - want).max() < 1.2e-2     # bf16 ulp at |x| ~ 2.2
     ld.drain(); d.para_load_close()
+
+
+def test_loader_process_mode_gpu(tmp_path, monkeypatch):
+    """Loader process → page-locked shared-memory ring → H2D on the copy stream → fused crop kernel, with real batch files."""
+    import numpy as np
+    from theanompi_b200.models.data.loader import ParaLoader
+    from theanompi_b200.models.data.proc_loader import ProcReader
+    arrs = []
+    for i in range(4):
+        a = np.random.RandomState(i).randint(0, 256, (8, 64, 64, 3), dtype=np.uint8)
+        np.save(str(tmp_path / ("b%d.npy" % i)), a)
+        arrs.append(a)
+    pr = ProcReader((8, 64, 64, 3), depth=2)
+    assert all(t.is_pinned() for t in pr.tensors)
+    ld = ParaLoader(pr.read, "cuda:0", (8, 64, 64, 3), (48, 48), mean=np.full((64, 64, 3), 127.5, np.float32), std_scale=1 / 255.0,
+                    depth=2, rand_crop=False, host_buffers=pr.tensors, on_close=pr.close)
+    try:
+        ld.request(str(tmp_path / "b0.npy"), "val")
+        for i in range(4):
+            if i + 1 < 4:
+                ld.request(str(tmp_path / ("b%d.npy" % (i + 1))), "val")
+            b = ld.get()
+            torch.cuda.synchronize()
+            want = ((arrs[i].astype(np.float32) - 127.5) / 255.0)[:, 8:56, 8:56, :]
+            assert np.abs(b.x.float().cpu().numpy() - want).max() < 4e-3, i
+    finally:
+        ld.close()

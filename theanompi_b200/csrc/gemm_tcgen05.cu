@@ -697,6 +697,14 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// fp32 operands of the tf32 path are described to the TMA unit as TFLOAT32: the copy engine then rounds every element to the
+// nearest tf32 value on its way into shared memory (the tensor core alone would truncate the low 13 mantissa bits, a biased
+// error that does not average out over K).  TMPI_TF32_TMA_ROUND=0 falls back to raw fp32 bits.
+static CUtensorMapDataType f32_map_type() {
+  static const bool rnd = [] { const char* e = getenv("TMPI_TF32_TMA_ROUND"); return !(e && e[0] == '0'); }();
+  return rnd ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+}
+
 // 2-D tensor map (bf16 or fp32 elements): dims {inner, outer}, row pitch in bytes, box {128 bytes, box_outer}, 128B swizzle,
 // zero OOB fill.
 static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_bytes, uint32_t box_outer, int esz = 2,
@@ -717,7 +725,7 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {(cuuint32_t)(128 / esz), box_outer};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+  CUresult r = get_encode()(&m, esz == 4 ? f32_map_type() : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled failed, code " + std::to_string((int)r));
@@ -948,7 +956,7 @@ static CUtensorMap make_im2col_map(const void* x, int N, int H, int W, int Ctot,
   int lower[2] = {-P, -P};
   int upper[2] = {P - (KW - 1), P - (KH - 1)};
   cuuint32_t estr[4] = {1u, (cuuint32_t)S, (cuuint32_t)S, 1u};
-  CUresult r = get_encode_im2col()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base),
+  CUresult r = get_encode_im2col()(&m, esz == 4 ? f32_map_type() : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(base),
                                    dims, strides, lower, upper, (cuuint32_t)(128 / esz), (cuuint32_t)pixels, estr,
                                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -974,7 +982,7 @@ static CUtensorMap make_weight_map(const void* w, int O, int taps, int Cg, int b
   cuuint64_t strides[2] = {(cuuint64_t)Cg * esz, (cuuint64_t)taps * Cg * esz};
   cuuint32_t box[3] = {(cuuint32_t)box_c, 1u, (cuuint32_t)box_o};
   cuuint32_t estr[3] = {1u, 1u, 1u};
-  CUresult r = get_encode()(&m, esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides,
+  CUresult r = get_encode()(&m, esz == 4 ? f32_map_type() : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides,
                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("tmpi_native: cuTensorMapEncodeTiled(3D weights) failed, code " + std::to_string((int)r));

@@ -183,17 +183,28 @@ class ImageNet_data(object):
 
     # ------------------------------------------------------------------ parallel loading
     def spawn_load(self):
-        """The reference spawns an MPI child here (``:226-267``); the B200 loader is a
-        thread + copy stream created in :meth:`para_load_init`."""
+        """The reference spawns an MPI child here (``:226-267``); here the loader (thread + copy stream, or with
+        ``TMPI_LOADER=process`` a child process filling a page-locked shared-memory ring) is created in
+        :meth:`para_load_init`, once the input geometry is known."""
         return None
 
     def para_load_init(self, device, input_width, input_height, rand_crop, batch_crop_mirror,
-                       out_dtype=None, depth=2):
+                       out_dtype=None, depth=2, mode=None):
+        """``mode='thread'`` (default): loader thread + pinned ring in this process.  ``mode='process'`` (or
+        ``TMPI_LOADER=process``): a separate loader process fills a page-locked shared-memory ring (see ``proc_loader.py``) —
+        the reference's ``proc_load_mpi.py`` child, minus its second CUDA context."""
         from .loader import ParaLoader
         raw_shape = (self.file_batch_size, self.height, self.width, self.channels)
-        self.loader = ParaLoader(self.read, device, raw_shape, (input_height, input_width),
-                                 mean=self.rawdata[4], std_scale=1.0 / 255.0 / self.rawdata[5], out_dtype=out_dtype,
-                                 depth=depth, rand_crop=rand_crop, batch_crop_mirror=batch_crop_mirror)
+        mode = mode or os.environ.get("TMPI_LOADER", "thread")
+        kw = dict(mean=self.rawdata[4], std_scale=1.0 / 255.0 / self.rawdata[5], out_dtype=out_dtype, depth=depth,
+                  rand_crop=rand_crop, batch_crop_mirror=batch_crop_mirror)
+        if mode == "process":
+            from .proc_loader import ProcReader
+            self.proc_reader = ProcReader(raw_shape, depth=depth, seed=self._seed)
+            self.loader = ParaLoader(self.proc_reader.read, device, raw_shape, (input_height, input_width),
+                                     host_buffers=self.proc_reader.tensors, on_close=self.proc_reader.close, **kw)
+        else:
+            self.loader = ParaLoader(self.read, device, raw_shape, (input_height, input_width), **kw)
         return self.loader
 
     def para_load_close(self):

@@ -44,7 +44,7 @@ class LoadedBatch(object):
 class ParaLoader(object):
     def __init__(self, read_fn, device, raw_shape, crop_hw, mean, std_scale=1.0 / 255.0,
                  out_dtype=None, depth=2, rand_crop=True, batch_crop_mirror=False, seed=1234,
-                 threaded=True):
+                 threaded=True, host_buffers=None, on_close=None):
         self.read_fn = read_fn
         self.device = torch.device(device)
         self.cuda = self.device.type == "cuda"
@@ -62,7 +62,14 @@ class ParaLoader(object):
         else:
             self.std_scale = float(std_scale)
         pin = self.cuda
-        self.host = [torch.empty(self.raw_shape, dtype=torch.uint8, pin_memory=pin) for _ in range(depth)]
+        self._on_close = on_close
+        if host_buffers is not None:                     # ring owned by a loader process (shared memory, page-locked)
+            assert len(host_buffers) == depth and all(tuple(t.shape) == self.raw_shape for t in host_buffers)
+            self.host = list(host_buffers)
+            self._ext_host = True
+        else:
+            self.host = [torch.empty(self.raw_shape, dtype=torch.uint8, pin_memory=pin) for _ in range(depth)]
+            self._ext_host = False
         self.host_offs = [torch.empty((N, 2), dtype=torch.int32, pin_memory=pin) for _ in range(depth)]
         self.host_flip = [torch.empty((N,), dtype=torch.uint8, pin_memory=pin) for _ in range(depth)]
         if self.cuda:
@@ -97,6 +104,10 @@ class ParaLoader(object):
         if not (isinstance(src, torch.Tensor) and src.dtype == torch.uint8 and tuple(src.shape) == self.raw_shape
                 and (not self.cuda or src.is_pinned())):
             src = self.host[s]
+        if self.cuda and self._ext_host and src is self.host[s]:
+            # the ring slot is refilled by another process as soon as we request the next file: the DMA out of it must have
+            # finished before this slot comes round again — recorded below, awaited at the top of the next _produce(s)
+            pass
         offs, flips = draw_crops(N, (H, W), self.crop_hw, mode, self.rand_crop, self.batch_crop_mirror, self.rs)
         self.host_offs[s].numpy()[...] = offs
         self.host_flip[s].numpy()[...] = flips
@@ -184,3 +195,8 @@ class ParaLoader(object):
             self._req.put(None)
             self._thread.join(timeout=10)
             self._thread = None
+        if self.cuda:
+            torch.cuda.synchronize(self.device)
+        if self._on_close is not None:
+            self._on_close()
+            self._on_close = None

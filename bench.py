@@ -248,6 +248,7 @@ def emit(args, world, K, Wm, dev_stats, e2e_stats, extra, model_name, inp, batch
                     "spread_pct": dev_stats["spread_pct"], "reported": "median"},
         "config": {"model": cls, "global_batch": batch * n_train_gpus, "seq_len": None, "input": inp,
                    "parallelism": "dp%d" % n_train_gpus, "rule": rule.upper(), "exch_strategy": strategy,
+                   "push_master": os.environ.get("TMPI_PUSH_MASTER", "0") == "1",
                    "cuda_graph": not args.no_graph, "overlap": not args.no_overlap,
                    "l2": "per-step working set (weights + grads + momentum + activations) >> 126 MB L2; no flush"},
         "clocks": clocks,
@@ -340,8 +341,9 @@ def run_easgd(args, rank, world, local):
     if rank == 0:
         from theanompi_b200.easgd_server import EASGD_Server
         server = EASGD_Server("cuda%d" % local)
-        full = dict(verbose=False, rank=0, size=1, no_paraload=True, device=str(server.ctx), mname=cls,
-                    arena_allocator=server.arena_allocator(), **cfg)
+        full = dict(cfg)
+        full.update(verbose=False, rank=0, size=1, no_paraload=True, device=str(server.ctx), mname=cls,
+                    arena_allocator=server.arena_allocator())
         model = Model(full)
         server.build(model)
         c0 = model.arena.W.clone()
@@ -369,8 +371,9 @@ def run_easgd(args, rank, world, local):
 
     from theanompi_b200.easgd_worker import EASGD_Worker
     worker = EASGD_Worker("cuda%d" % local)
-    full = dict(verbose=False, rank=rank - 1, size=nw, mname=cls, device=str(worker.ctx), arena_allocator=worker.arena_allocator(),
-                cuda_graph=not args.no_graph, **cfg)
+    full = dict(cfg)
+    full.update(verbose=False, rank=rank - 1, size=nw, mname=cls, device=str(worker.ctx), arena_allocator=worker.arena_allocator(),
+                cuda_graph=not args.no_graph)
     model = Model(full)
     worker.build(model, full)
     rec, exch = worker.recorder, worker.exchanger
@@ -475,8 +478,9 @@ def run_gosgd(args, rank, world, local):
     K, Wm, R = args.steps, max(3, args.warmup), max(1, args.repeats)
     modfile, cls, cfg, inp = model_cfg(args, args.model, world)
     worker = GOSGD_Worker("cuda%d" % local)
-    full = dict(verbose=False, rank=rank, size=world, mname=cls, device=str(worker.ctx), arena_allocator=worker.arena_allocator(),
-                gosgd_p=args.gosgd_p, cuda_graph=not args.no_graph, **cfg)
+    full = dict(cfg)
+    full.update(verbose=False, rank=rank, size=world, mname=cls, device=str(worker.ctx), arena_allocator=worker.arena_allocator(),
+                gosgd_p=args.gosgd_p, cuda_graph=not args.no_graph)
     model = getattr(importlib.import_module(modfile), cls)(full)
     worker.build(model, full)
     rec, exch = worker.recorder, worker.exchanger

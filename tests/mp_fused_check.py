@@ -86,6 +86,29 @@ def main():
                 eu = float((arena.U - u_ref).abs().max())
                 assert eu < tol * 10, eu
 
+    # owner-keeps-master: the fused kernel ships only the bf16 shadow of an updated slice; the fp32 master copies of non-owners
+    # go stale until push_master_slices() re-synchronises them
+    for algo in [a for a in algos if a != "oneshot"]:
+        reset(8)
+        w_ref, u_ref = reference_step(False)
+        gc.fused_allreduce_sgd(arena, 0, arena.numel, 0.9, False, algo=algo, max_blocks=24, push_master=False)
+        torch.cuda.synchronize(); dist.barrier()
+        hl = [torch.empty_like(arena.H) for _ in range(world)]
+        dist.all_gather(hl, arena.H.clone())
+        assert all(torch.equal(hl[0], x) for x in hl), ("shadows differ", algo)
+        assert float((arena.H.float() - w_ref).abs().max()) < 5e-3, algo
+        nb = arena.numel // 1024
+        per = (nb + world - 1) // world
+        lo_, hi_ = rank * per * 1024, min(arena.numel, (rank + 1) * per * 1024)
+        assert float((arena.W[lo_:hi_] - w_ref[lo_:hi_]).abs().max()) < 1e-5, ("owner slice", algo)
+        gc.push_master_slices(arena, 0, arena.numel)
+        torch.cuda.synchronize(); dist.barrier()
+        assert float((arena.W - w_ref).abs().max()) < 1e-5, ("after push_master_slices", algo)
+        wl = [torch.empty_like(arena.W) for _ in range(world)]
+        dist.all_gather(wl, arena.W.clone())
+        assert all(torch.equal(wl[0], x) for x in wl), ("masters differ after sync", algo)
+        results["owner_keeps_master_" + algo] = True
+
     # sub-range (bucket) exchange leaves the rest untouched
     reset(9)
     w0 = arena.W.clone()

@@ -123,6 +123,8 @@ def test_linear_small_batch_splitk_forward(B, I, O, relu):
 
 @pytest.mark.parametrize("cfg", [
     dict(N=4, H=31, W=31, C=3, O=32, k=11, s=4, p=0),      # conv1-like (C=3, K % 8 != 0)
+    dict(N=3, H=64, W=64, C=3, O=64, k=7, s=2, p=3),       # ResNet / GoogLeNet stem: padding folded into the space-to-depth image
+    dict(N=2, H=33, W=37, C=3, O=16, k=5, s=2, p=2),       # odd sizes, padded, strided few-channel conv
     dict(N=3, H=13, W=13, C=64, O=96, k=3, s=1, p=1),
     dict(N=2, H=14, W=14, C=32, O=48, k=5, s=1, p=2),
     dict(N=2, H=12, W=12, C=64, O=32, k=1, s=1, p=0),      # 1x1
@@ -420,3 +422,47 @@ def test_adam_flat_matches_torch():
     torch.cuda.synchronize()
     for p, q in zip(ref_p, arena.params):
         assert rel_err(q, p) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_inception_node_matches_composition(dtype):
+    """The fused inception node (slice-writing epilogues, 4 streams, native gradient merge) against the fp32 torch composition
+    conv / pool / cat of the same weights."""
+    from theanompi_b200.ops import precision
+    from theanompi_b200.ops.inception import inception
+    old = precision.precision()
+    precision.set_precision("tf32" if dtype == torch.float32 else "bf16")
+    try:
+        torch.manual_seed(17)
+        N, H, W, C = 8, 14, 14, 192
+        n1, nr3, n3, nr5, n5, npj = 64, 96, 128, 16, 32, 32
+        x = torch.randn(N, H, W, C, device=DEV).to(dtype).requires_grad_(True)
+        shapes = [(n1, 1, 1, C), (nr3, 1, 1, C), (n3, 3, 3, nr3), (nr5, 1, 1, C), (n5, 5, 5, nr5), (npj, 1, 1, C)]
+        ws = [(torch.randn(s, device=DEV) * 0.05).to(dtype).requires_grad_(True) for s in shapes]
+        bs = [torch.randn(s[0], device=DEV).requires_grad_(True) for s in shapes]
+        ps = []
+        for w, b in zip(ws, bs):
+            ps += [w, b]
+        y = inception(x, tuple(ps))
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        torch.cuda.synchronize()
+        # fp32 reference, ReLU masks taken from our own outputs where they are visible (final convs)
+        F = torch.nn.functional
+        xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = [w.detach().float().permute(0, 3, 1, 2).requires_grad_(True) for w in ws]
+        br = [b.detach().clone().requires_grad_(True) for b in bs]
+        a = torch.relu(F.conv2d(xr, wr[0], br[0]))
+        b_ = torch.relu(F.conv2d(torch.relu(F.conv2d(xr, wr[1], br[1])), wr[2], br[2], padding=1))
+        c = torch.relu(F.conv2d(torch.relu(F.conv2d(xr, wr[3], br[3])), wr[4], br[4], padding=2))
+        d = torch.relu(F.conv2d(F.max_pool2d(xr, 3, 1, 1), wr[5], br[5]))
+        yr = torch.cat([a, b_, c, d], 1)
+        yr.backward(dy.float().permute(0, 3, 1, 2))
+        tol = 3e-2 if dtype == torch.bfloat16 else 5e-3
+        assert rel_err(y, yr.permute(0, 2, 3, 1)) < tol
+        assert rel_err(x.grad, xr.grad.permute(0, 2, 3, 1)) < 2 * tol
+        for i in range(6):
+            assert rel_err(ws[i].grad, wr[i].grad.permute(0, 2, 3, 1)) < 2 * tol, i
+            assert rel_err(bs[i].grad, br[i].grad) < 2 * tol, i
+    finally:
+        precision.set_precision(old)

@@ -90,6 +90,7 @@ def test_linear_tf32_fwd_bwd():
     dict(N=4, H=13, W=13, C=256, O=384, k=3, s=1, p=1, g=1),          # AlexNet conv3
     dict(N=4, H=27, W=27, C=96, O=256, k=5, s=1, p=2, g=2),           # AlexNet conv2 (two groups, one launch)
     dict(N=2, H=57, W=57, C=3, O=96, k=11, s=4, p=0, g=1),            # AlexNet conv1 (space-to-depth rewrite), no input grad
+    dict(N=2, H=64, W=64, C=3, O=64, k=7, s=2, p=3, g=1),             # ResNet / GoogLeNet stem: padded space-to-depth rewrite
     dict(N=2, H=14, W=14, C=36, O=40, k=3, s=1, p=1, g=1),            # channel counts that are not multiples of 32
     dict(N=2, H=16, W=16, C=3, O=64, k=3, s=1, p=1, g=1),             # VGG first layer (explicit im2col path)
     dict(N=2, H=15, W=15, C=32, O=64, k=3, s=2, p=1, g=1),            # strided: dgrad through col2im

@@ -352,7 +352,12 @@ def run_torch_best(args, rank, world, local, K, Wm, ClockSampler, published):
             "clocks": clocks,
             "e2e": {"value": ms2 * per / 1000.0, "unit": "s/5120img", "ms_per_step": ms2, "h2d_bytes_per_step": pinned.numel(),
                     "d2h_bytes_per_step": 4},
-            "gpu_launches": 0, "final_loss": lv}))
+            "gpu_launches": 0, "final_loss": lv}), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a process group whose collectives were captured into a CUDA graph can hang in destroy_process_group(): leave at once
+        import os
+        import sys
+        barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     return 0

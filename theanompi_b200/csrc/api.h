@@ -31,6 +31,9 @@ struct FusedArgs {
   int wire16;                                        // gradients travel as bf16 (cast into the wire region first)
   int pre_reduced;                                   // the range's gradients were already reduce-scattered into their owner's G by the
                                                      // wgrad GEMM epilogues (gemm_rs_*): skip the gather, zero G after use
+  int push_master = 1;                               // two-shot: 1 = push the updated fp32 master slice AND the bf16 shadow to every peer;
+                                                     // 0 = owner keeps the master (peers receive only the bf16 compute shadow — a third of
+                                                     // the all-gather bytes); push_master_slices() re-synchronises W on demand
 };
 
 struct ReduceArgs {
@@ -45,6 +48,7 @@ struct ReduceArgs {
 
 // ---- gemm_tcgen05.cu
 void gemm_set_debug(int flags);
+void gemm_set_bulk(int mask);      // epilogue through the bulk copy engine: bit0 stores, bit1 split-K adds, bit2 reduce-scatter adds; -1 = env
 // Reduce-scatter fused into the wgrad GEMM epilogue: register the peer views of the gradient region and the tensors whose
 // fp32 GEMM output (C pointer inside [c_lo, c_hi)) must be red.add-ed into the OWNER rank's G instead of stored locally.
 // Ownership = the two-shot exchange kernel's partition of the bucket [blo, blo + world * per) in 1024-element blocks.
@@ -69,7 +73,7 @@ void conv_wgrad2_bf16(const void* dy0, const void* dy1, const void* x, void* dw0
                       int c_off1, int Cg, int KH, int KW, int Ho, int Wo, int S, int P, int O, long long ldy, cudaStream_t st, int tf32 = 0);
 
 // ---- nn_kernels.cu
-void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st);
+void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int P, cudaStream_t st);
 void s2d_filter(const void* src, void* dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, cudaStream_t st);
 void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cudaStream_t st);
 void lrn_fwd(const void* x, void* y, long long rows, int C, int n, float k, float alpha, float beta, cudaStream_t st);
@@ -112,7 +116,7 @@ void im2col_f32(const void* x, void* col, int N, int H, int W, int Ctot, int c_o
 void col2im_f32(const void* dcol, void* dx, int N, int H, int W, int Ctot, int c_off, int Cg, int KH, int KW, int Ho, int Wo, int s, int p,
                 long long ldcol, cudaStream_t st);
 void pad_rows_f32(const void* src, void* dst, long long rows, int cols, long long src_ld, long long dst_ld, cudaStream_t st);
-void space_to_depth_f32(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st);
+void space_to_depth_f32(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int P, cudaStream_t st);
 void s2d_filter_pack_f32(const void* src, void* dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, cudaStream_t st);
 
 // ---- bn_kernels.cu: batch norm (+ residual)(+ ReLU) forward / backward, residual add  (f32: fp32 activations, else bf16)
@@ -121,6 +125,7 @@ void bn_forward(const void* x, const void* res, void* y, const void* gamma, cons
 void bn_backward(const void* x, const void* dy, const void* y, void* dx, void* dres, const void* gamma, const void* mean, const void* rstd,
                  void* dgamma, void* dbeta, long long R, int C, int relu, int f32, cudaStream_t st);
 void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cudaStream_t st);
+void add4_tensors(const void* a, const void* b, const void* c, const void* d, void* y, long long n, int f32, cudaStream_t st);
 
 // ---- comm_kernels.cu
 void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, float mu,
@@ -128,6 +133,8 @@ void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group,
 void adam_flat(void* W, const void* G, void* M, void* V, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, void* step,
                float b1, float b2, float eps, long long lo, long long hi, cudaStream_t st);
 void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStream_t st);
+// every rank pushes the fp32 master weights of the slice it owns in the two-shot partition of [lo, hi) to all peers
+void push_master_slices(const FusedArgs& a, int max_blocks, cudaStream_t st);
 void allreduce_flat(const ReduceArgs& a, int algo, int max_blocks, cudaStream_t st);
 void device_barrier(const CommCtx& c, cudaStream_t st);
 void easgd_elastic(void* w, void* h, void* center, float alpha, long long n, int max_blocks, int lockfree, cudaStream_t st);

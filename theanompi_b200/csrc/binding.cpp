@@ -48,6 +48,7 @@ PYBIND11_MODULE(_tmpi_native, m) {
 
   // ---------------------------------------------------------------- GEMM
   m.def("gemm_set_debug", &gemm_set_debug);
+  m.def("gemm_set_bulk", &gemm_set_bulk);
   m.def("gemm_rs_add_range", [](ptr_t c_lo, ptr_t c_hi, long long blo, long long per) { gemm_rs_add_range(P(c_lo), P(c_hi), blo, per); });
   m.def("gemm_rs_clear", &gemm_rs_clear);
   m.def("gemm_plan_splits", &gemm_plan_splits);
@@ -88,8 +89,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
   }, py::arg("dy0"), py::arg("dy1"), py::arg("x"), py::arg("dw0"), py::arg("dw1"), py::arg("N"), py::arg("H"), py::arg("W"), py::arg("Ctot"),
      py::arg("c_off0"), py::arg("c_off1"), py::arg("Cg"), py::arg("KH"), py::arg("KW"), py::arg("Ho"), py::arg("Wo"), py::arg("S"),
      py::arg("P"), py::arg("O"), py::arg("ldy"), py::arg("st"), py::arg("tf32") = 0);
-  m.def("space_to_depth", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, ptr_t st) {
-    space_to_depth(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, S_(st)); });
+  m.def("space_to_depth", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int Pd, ptr_t st) {
+    space_to_depth(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, Pd, S_(st)); });
   m.def("s2d_filter", [](ptr_t src, ptr_t dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, int dir, ptr_t st) {
     s2d_filter(P(src), P(dst), O, KH, KW, C, S, KHs, KWs, Cp, dir, S_(st)); });
   m.def("conv_weight_flip", [](ptr_t w, ptr_t wt, int O, int KH, int KW, int Cg, ptr_t st) { conv_weight_flip(P(w), P(wt), O, KH, KW, Cg, S_(st)); });
@@ -150,8 +151,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
                          long long ldcol, ptr_t st) { col2im_f32(P(dcol), P(dx), N, H, W, Ctot, c_off, Cg, KH, KW, Ho, Wo, s, p, ldcol, S(st)); });
   m.def("pad_rows_f32", [](ptr_t src, ptr_t dst, long long rows, int cols, long long src_ld, long long dst_ld, ptr_t st) {
     pad_rows_f32(P(src), P(dst), rows, cols, src_ld, dst_ld, S(st)); });
-  m.def("space_to_depth_f32", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, ptr_t st) {
-    space_to_depth_f32(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, S_(st)); });
+  m.def("space_to_depth_f32", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int Pd, ptr_t st) {
+    space_to_depth_f32(P(x), P(y), N, H, W, C, S, Hs, Ws, Cp, Pd, S_(st)); });
   m.def("s2d_filter_pack_f32", [](ptr_t src, ptr_t dst, int O, int KH, int KW, int C, int S, int KHs, int KWs, int Cp, ptr_t st) {
     s2d_filter_pack_f32(P(src), P(dst), O, KH, KW, C, S, KHs, KWs, Cp, S_(st)); });
 
@@ -163,6 +164,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
   m.def("bn_backward", [](ptr_t x, ptr_t dy, ptr_t y, ptr_t dx, ptr_t dres, ptr_t gamma, ptr_t mean, ptr_t rstd, ptr_t dgamma, ptr_t dbeta,
                           long long R, int C, int relu, int f32, ptr_t st) {
     bn_backward(P(x), P(dy), P(y), P(dx), P(dres), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), R, C, relu, f32, S(st)); });
+  m.def("add4_tensors", [](ptr_t a, ptr_t b, ptr_t c, ptr_t d, ptr_t y, long long n, int f32, ptr_t st) {
+    add4_tensors(P(a), P(b), P(c), P(d), P(y), n, f32, S(st)); });
   m.def("add_tensors", [](ptr_t a, ptr_t b, ptr_t y, long long n, int f32, ptr_t st) { add_tensors(P(a), P(b), P(y), n, f32, S(st)); });
 
   // ---------------------------------------------------------------- optimizer / legacy kernels
@@ -219,9 +222,10 @@ PYBIND11_MODULE(_tmpi_native, m) {
       .def("fused_allreduce_sgd",
            [](PyComm& c, long long w_off, long long g_off, long long u_off, long long h_off, long long wire_off, ptr_t block_group,
               std::vector<float> lr_mult, std::vector<float> wd, std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k,
-              long long lo, long long hi, int wire16, int algo, int max_blocks, ptr_t st, int pre_reduced) {
+              long long lo, long long hi, int wire16, int algo, int max_blocks, ptr_t st, int pre_reduced, int push_master) {
              FusedArgs a;
              a.pre_reduced = pre_reduced;
+             a.push_master = push_master;
              a.ctx = c.pa->ctx();
              a.w_off = w_off; a.g_off = g_off; a.u_off = u_off; a.h_off = h_off; a.wire_off = wire_off;
              a.block_group = (const uint8_t*)P(block_group);
@@ -230,7 +234,19 @@ PYBIND11_MODULE(_tmpi_native, m) {
              fused_allreduce_sgd(a, algo, max_blocks, S(st));
            }, py::arg("w_off"), py::arg("g_off"), py::arg("u_off"), py::arg("h_off"), py::arg("wire_off"), py::arg("block_group"),
            py::arg("lr_mult"), py::arg("wd"), py::arg("exch"), py::arg("lr_ptr"), py::arg("mu"), py::arg("nesterov"), py::arg("inv_k"),
-           py::arg("lo"), py::arg("hi"), py::arg("wire16"), py::arg("algo"), py::arg("max_blocks"), py::arg("st"), py::arg("pre_reduced") = 0)
+           py::arg("lo"), py::arg("hi"), py::arg("wire16"), py::arg("algo"), py::arg("max_blocks"), py::arg("st"), py::arg("pre_reduced") = 0,
+           py::arg("push_master") = 1)
+      .def("push_master_slices",
+           [](PyComm& c, long long w_off, ptr_t block_group, std::vector<float> lr_mult, std::vector<float> wd, std::vector<int> exch,
+              long long lo, long long hi, int max_blocks, ptr_t st) {
+             FusedArgs a;
+             a.pre_reduced = 0; a.ctx = c.pa->ctx();
+             a.w_off = w_off; a.g_off = a.u_off = a.wire_off = 0; a.h_off = -1;
+             a.block_group = (const uint8_t*)P(block_group);
+             a.tab = make_table(lr_mult, wd, exch);
+             a.lr_ptr = nullptr; a.mu = 0.f; a.nesterov = 0; a.inv_k = 1.f; a.lo = lo; a.hi = hi; a.wire16 = 0;
+             push_master_slices(a, max_blocks, S(st));
+           })
       .def("configure_gemm_rs", [](PyComm& c, long long g_off) {
              // peer views of the gradient region for the reduce-scatter GEMM epilogue
              const CommCtx x = c.pa->ctx();

@@ -206,6 +206,20 @@ __global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const
   VecIO<T>::st(y + idx * N, av);
 }
 
+// y = a + b + c + d (gradient merge of the four inception branches)
+template <typename T>
+__global__ void __launch_bounds__(256) add4_kernel(const T* __restrict__ a, const T* __restrict__ b, const T* __restrict__ c, const T* __restrict__ d,
+                                                  T* __restrict__ y, long long total_vec) {
+  constexpr int N = VecIO<T>::N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total_vec) return;
+  float av[N], bv[N], cv[N], dv[N];
+  VecIO<T>::ld(a + idx * N, av); VecIO<T>::ld(b + idx * N, bv); VecIO<T>::ld(c + idx * N, cv); VecIO<T>::ld(d + idx * N, dv);
+#pragma unroll
+  for (int i = 0; i < N; ++i) av[i] = (av[i] + bv[i]) + (cv[i] + dv[i]);
+  VecIO<T>::st(y + idx * N, av);
+}
+
 // ---------------------------------------------------------------- launchers (f32 = 1: fp32 activations, else bf16)
 void bn_forward(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* mean, void* rstd, void* run_mean,
                 void* run_var, void* scratch /*2*C floats*/, long long R, int C, float momentum, float eps, int training, int relu, int f32,
@@ -250,6 +264,16 @@ void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cu
   if (f32) add_kernel<float><<<grid1(tv, 256), 256, 0, st>>>((const float*)a, (const float*)b, (float*)y, tv);
   else add_kernel<__nv_bfloat16><<<grid1(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)y, tv);
   count_launch(); TMPI_CHECK_LAUNCH("add_tensors"); ::tmpi::check_capture(st, "add_tensors");
+}
+
+void add4_tensors(const void* a, const void* b, const void* c, const void* d, void* y, long long n, int f32, cudaStream_t st) {
+  const int N = f32 ? 4 : 8;
+  if (n % N) throw std::runtime_error("add4_tensors: numel must be a multiple of the 16-byte vector width");
+  const long long tv = n / N;
+  if (f32) add4_kernel<float><<<grid1(tv, 256), 256, 0, st>>>((const float*)a, (const float*)b, (const float*)c, (const float*)d, (float*)y, tv);
+  else add4_kernel<__nv_bfloat16><<<grid1(tv, 256), 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (const __nv_bfloat16*)c,
+                                                                  (const __nv_bfloat16*)d, (__nv_bfloat16*)y, tv);
+  count_launch(); TMPI_CHECK_LAUNCH("add4_tensors"); ::tmpi::check_capture(st, "add4_tensors");
 }
 
 }  // namespace tmpi

@@ -321,14 +321,16 @@ __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const Fused
       sgd4(w, uu, gs[u], h, a.tab.lr_mult[grp[u]], a.tab.wd[grp[u]]);
       *reinterpret_cast<float4*>(U_ + i) = uu;
       const uint2 wh = pack_bf16x4(w);
+      const bool push_w = a.push_master || a.h_off < 0;       // owner-keeps-master needs a shadow for the peers to compute with
       if (use_nvls) {
-        mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
+        if (push_w) mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
+        else *reinterpret_cast<float4*>(W + i) = w;
         if (a.h_off >= 0) mc_st_u2(reinterpret_cast<char*>(a.ctx.mc_arena) + a.h_off + i * 2, wh);
       } else {
 #pragma unroll
         for (int p = 0; p < kMaxRanks; ++p) {
           if (p < Wn) {
-            st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
+            if (push_w || p == R) st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
             if (a.h_off >= 0) st_u2(region<__nv_bfloat16>(a.ctx, p, a.h_off) + i, wh);
           }
         }
@@ -368,6 +370,34 @@ void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStrea
     else fused_twoshot_sgd_kernel<4><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
   }
   count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd"); ::tmpi::check_capture(st, "fused_allreduce_sgd");
+}
+
+// every rank pushes the fp32 master of the slice it owns (two-shot partition of [lo, hi)) to all peers: re-synchronises W after
+// steps that ran with push_master = 0 (before a checkpoint / weight averaging / anything that reads W on a non-owner)
+__global__ void __launch_bounds__(kThreads) push_master_kernel(const FusedArgs a) {
+  const long long blo = a.lo / kArenaBlock, bhi = a.hi / kArenaBlock;
+  const long long per = (bhi - blo + a.ctx.world - 1) / a.ctx.world;
+  const int R = a.ctx.rank;
+  const long long s0 = blo + R * per, s1 = min(bhi, s0 + per);
+  block_barrier(a.ctx);
+  const float* W = region<float>(a.ctx, R, a.w_off);
+  for (long long b = s0 + blockIdx.x; b < s1; b += gridDim.x) {
+    if (!a.tab.exch[a.block_group[b]]) continue;
+    const long long i = b * kArenaBlock + threadIdx.x * 4;
+    const float4 w = *reinterpret_cast<const float4*>(W + i);
+#pragma unroll
+    for (int p = 0; p < kMaxRanks; ++p)
+      if (p < a.ctx.world && p != R) st_f4(region<float>(a.ctx, p, a.w_off) + i, w);
+  }
+  block_barrier(a.ctx);
+}
+void push_master_slices(const FusedArgs& a, int max_blocks, cudaStream_t st) {
+  if (a.lo % kArenaBlock || a.hi % kArenaBlock) throw std::runtime_error("push_master_slices: range must be block aligned");
+  const long long nb = (a.hi - a.lo) / kArenaBlock;
+  if (nb <= 0) return;
+  const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
+  push_master_kernel<<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a);
+  count_launch(); TMPI_CHECK_LAUNCH("push_master_slices"); ::tmpi::check_capture(st, "push_master_slices");
 }
 
 // ============================================================================ plain flat allreduce (sum * scale) src region → dst region

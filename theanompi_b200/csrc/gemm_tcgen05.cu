@@ -99,6 +99,9 @@ struct Params {
   unsigned rs_blo = 0, rs_per = 1;
   long long rs_e0 = 0;  // element index of C[0, 0] inside the G region
   float* rs_g[kMaxRanks] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // epilogue through the bulk copy engine (cp.async.bulk / cp.reduce.async.bulk, one 64–128 byte row segment per lane):
+  // bit 0 plain stores, bit 1 split-K reductions, bit 2 reduce-scatter reductions over NVLink (TMPI_GEMM_BULK, see launch())
+  int bulk = 0;
 };
 
 // owner-rank address of element e of the gradient region (no dynamic indexing of the kernel-parameter array)
@@ -182,6 +185,18 @@ __device__ __forceinline__ void tma_load_im2col(uint32_t dst, const CUtensorMap*
       "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"((uint16_t)off_w), "h"((uint16_t)off_h) : "memory");
 }
+// Bulk (TMA engine) epilogue ops: one contiguous row segment shared → global per call; the reduce form adds fp32 into global
+// (or peer-mapped) memory as ONE packet per segment instead of 16-byte vector atomics.
+__device__ __forceinline__ void bulk_store(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(void* gdst, uint32_t ssrc, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst), "r"(ssrc), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -608,6 +623,30 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
               for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             }
             __syncwarp();
+            const int bulk_kind = p.rs_world > 0 ? 4 : (p.atomic_out ? 2 : 1);
+            if (p.bulk & bulk_kind) {
+              // one row segment (32 columns) per lane through the bulk copy engine: the staging row this lane just wrote is
+              // the source; generic-proxy writes are fenced into the async proxy first
+              fence_proxy_async();
+              const long long gm = (long long)mbase + row;
+              if (gm < p.M) {
+                const uint32_t ssrc = smem_u32(wstage + (size_t)lane * pitch);
+                const uint32_t nbytes = (uint32_t)(32 * esz);
+                if (p.rs_world > 0) {
+                  bool local;
+                  float* d = rs_addr(p, p.rs_e0 + gm * p.ldc + nb, local);
+                  bulk_reduce_add_f32(d, ssrc, nbytes);
+                } else if (p.atomic_out) {
+                  bulk_reduce_add_f32(Cg_ptr + ((long long)gm * p.ldc + nb) * esz, ssrc, nbytes);
+                } else {
+                  bulk_store(Cg_ptr + ((long long)gm * p.ldc + nb) * esz, ssrc, nbytes);
+                }
+              }
+              bulk_commit();
+              bulk_wait_read();                                          // staging row may be overwritten by the next chunk
+              __syncwarp();
+              continue;
+            }
             uint8_t* gbase = Cg_ptr + (long long)nb * esz + (long long)lv * 16;
             for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
               const int rr = r0 + lr;                                  // row inside this warp's 32-row band
@@ -673,6 +712,7 @@ gemm_tcgen05(const __grid_constant__ CUtensorMap tmap_a0, const __grid_constant_
       }
     }
   }
+  if (warp >= 2 && p.bulk) bulk_wait_all();                // bulk stores / reductions have landed before the kernel retires
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, C::TMEM_COLS); }
@@ -735,6 +775,11 @@ static CUtensorMap make_tmap(const void* ptr, uint64_t inner, uint64_t outer, ui
 }
 
 static int g_dbg = 0;
+static int g_bulk = -1;            // gemm_set_bulk(): -1 = TMPI_GEMM_BULK env (default 4: reduce-scatter reductions only)
+static int bulk_default() {
+  static const int v = [] { const char* e = getenv("TMPI_GEMM_BULK"); return e ? atoi(e) : 4; }();
+  return v;
+}
 
 // Split-K factor for a persistent grid of `sms` CTAs walking equal-length tiles round-robin: minimise
 // waves x (k-blocks per slice + per-tile overhead).  A plain ceil(sms / tiles) overshoots the machine by a few tiles
@@ -760,6 +805,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, Params& p, int 
                    const CUtensorMap* ta1 = nullptr, const CUtensorMap* tb1 = nullptr) {
   using C = Cfg<T, BN, MT>;
   p.dbg = g_dbg;
+  p.bulk = g_bulk < 0 ? bulk_default() : g_bulk;
   if (!ta1) { p.groups = 1; p.C1 = nullptr; p.bias1 = nullptr; }
   static bool attr_set = false;
   if (!attr_set) {
@@ -789,6 +835,7 @@ static bool use_tall_tiles(long long M, int nt, int eligible, int sms) {
 }  // namespace gemm
 
 void gemm_set_debug(int flags) { gemm::g_dbg = flags; }
+void gemm_set_bulk(int mask) { gemm::g_bulk = mask; }
 
 // ---- reduce-scatter epilogue registry (see api.h)
 namespace gemm {

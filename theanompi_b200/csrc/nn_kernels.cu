@@ -914,30 +914,33 @@ void conv_weight_flip(const void* w, void* wt, int O, int KH, int KW, int Cg, cu
 // row S*i+dy starting at j*S*C — a strided copy of short runs; threads sweep the row's output elements (coalesced stores).
 template <int SCT>
 __global__ void __launch_bounds__(256) space_to_depth_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int N, int H,
-                                                             int W, int C, int S, int Hs, int Ws, int Cp) {
+                                                             int W, int C, int S, int Hs, int Ws, int Cp, int P) {
   // blockDim = (Cp, 256 / Cp): threadIdx.x = output channel cp, threadIdx.y strides over the pixels j of output row (n, i).
   // SCT > 0: S*C is a compile-time constant, so cp / SC and cp % SC are a multiply-shift (the generic version was
   // issue-bound on runtime divisions: 74 instructions per 2-byte element).
+  // P = zero padding of the ORIGINAL convolution, folded in here: output (i, j, (dy, dx, c)) reads x[S*i + dy - P, S*j + dx - P, c].
   const int i = blockIdx.x % Hs, n = blockIdx.x / Hs;
   const int SC = SCT > 0 ? SCT : S * C;
   const int WC = W * C;
   const int cp = threadIdx.x;
   const int dy = cp / SC, e = cp - dy * SC;
-  const bool chan_ok = cp < S * SC && (i * S + dy) < H;
+  const int h = i * S + dy - P;
+  const bool chan_ok = cp < S * SC && h >= 0 && h < H;
   __nv_bfloat16* orow = y + ((long long)n * Hs + i) * Ws * Cp + cp;
-  const __nv_bfloat16* irow = x + ((long long)n * H + (long long)i * S) * WC + (unsigned)(dy * WC + e);
+  const __nv_bfloat16* irow = x + ((long long)n * H + (chan_ok ? h : 0)) * WC;
   const __nv_bfloat16 zero = f_to_bf16(0.f);
+  const int shift = e - P * C;
   for (int j = threadIdx.y; j < Ws; j += blockDim.y) {
-    const int col = j * SC;
-    orow[(unsigned)(j * Cp)] = (chan_ok && col + e < WC) ? irow[col] : zero;
+    const int col = j * SC + shift;                      // element offset inside the image row
+    orow[(unsigned)(j * Cp)] = (chan_ok && col >= 0 && col < WC) ? irow[col] : zero;
   }
 }
-void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st) {
+void space_to_depth(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int P, cudaStream_t st) {
   if (Cp > 256) throw std::runtime_error("space_to_depth: more than 256 packed channels");
   const dim3 blk((unsigned)Cp, (unsigned)std::max(1, 256 / Cp));
   auto X = (const __nv_bfloat16*)x; auto Y = (__nv_bfloat16*)y;
-  if (S * C == 12) space_to_depth_kernel<12><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp);
-  else space_to_depth_kernel<0><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp);
+  if (S * C == 12) space_to_depth_kernel<12><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp, P);
+  else space_to_depth_kernel<0><<<(unsigned)N * Hs, blk, 0, st>>>(X, Y, N, H, W, C, S, Hs, Ws, Cp, P);
   count_launch(); TMPI_CHECK_LAUNCH("space_to_depth"); ::tmpi::check_capture(st, "space_to_depth");
 }
 

@@ -393,7 +393,7 @@ void pad_rows_f32(const void* src, void* dst, long long rows, int cols, long lon
 
 // ============================================================================ space-to-depth (strided few-channel first layer) — see nn_kernels.cu
 __global__ void space_to_depth_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int S, int Hs, int Ws,
-                                          int Cp) {
+                                          int Cp, int P) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * Hs * Ws * Cp;
   if (idx >= total) return;
@@ -403,13 +403,13 @@ __global__ void space_to_depth_f32_kernel(const float* __restrict__ x, float* __
   float v = 0.f;
   if (cp < S * S * C) {
     const int c = cp % C, d = cp / C, dy = d / S, dx = d % S;
-    const int h = i * S + dy, w = j * S + dx;
-    if (h < H && w < W) v = x[(((long long)n * H + h) * W + w) * C + c];
+    const int h = i * S + dy - P, w = j * S + dx - P;          // P: zero padding of the original convolution, folded in
+    if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((long long)n * H + h) * W + w) * C + c];
   }
   y[idx] = v;
 }
-void space_to_depth_f32(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, cudaStream_t st) {
-  space_to_depth_f32_kernel<<<grid_f((long long)N * Hs * Ws * Cp, 256), 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, S, Hs, Ws, Cp);
+void space_to_depth_f32(const void* x, void* y, int N, int H, int W, int C, int S, int Hs, int Ws, int Cp, int P, cudaStream_t st) {
+  space_to_depth_f32_kernel<<<grid_f((long long)N * Hs * Ws * Cp, 256), 256, 0, st>>>((const float*)x, (float*)y, N, H, W, C, S, Hs, Ws, Cp, P);
   count_launch(); TMPI_CHECK_LAUNCH("space_to_depth_f32"); ::tmpi::check_capture(st, "space_to_depth_f32");
 }
 // fp32 filter pack: ws[o, a, b, (dy*S+dx)*C + c] = w[o, S*a+dy, S*b+dx, c]   (the unpack direction is type-agnostic: s2d_filter dir 1)

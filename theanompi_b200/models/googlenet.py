@@ -59,11 +59,13 @@ class Incept(Layer):
             self.print_shape()
 
     def forward(self, x):
-        a = self.conv_1x1.forward(x)
-        b = self.conv_3x3.forward(self.conv_r3x3.forward(x))
-        c = self.conv_5x5.forward(self.conv_r5x5.forward(x))
-        d = self.conv_pj.forward(self.pool_3x3.forward(x))
-        return torch.cat([a, b, c, d], dim=-1)
+        # one autograd node for the whole module: branch outputs land in their channel slice of the concatenated tensor, the
+        # four branches run on four streams, the four input gradients are merged by one kernel (ops/inception.py)
+        from ..ops.inception import inception
+        ps = []
+        for l in (self.conv_1x1, self.conv_r3x3, self.conv_3x3, self.conv_r5x5, self.conv_5x5, self.conv_pj):
+            ps += [l.W.val, l.b.val]
+        return inception(x, tuple(ps))
 
 
 class Aux_tower(Layer):

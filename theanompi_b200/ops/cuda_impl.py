@@ -272,22 +272,24 @@ def _conv_fwd_group(x, w, b, y, o_off, c_off, Cg, s, p, relu):
 
 
 def _s2d_geom(H, W, C, KH, KW, stride, pad):
-    """Geometry of the space-to-depth rewrite of a strided few-channel conv, or None when it does not apply."""
-    if not (CONV_MODE == "implicit" and C < 8 and C % 4 != 0 and stride > 1 and pad == 0):
+    """Geometry of the space-to-depth rewrite of a strided few-channel conv, or None when it does not apply.  The zero padding
+    of the original convolution is folded into the space-to-depth image (the kernel reads x[S*i + dy - pad, ...])."""
+    if not (CONV_MODE == "implicit" and C < 8 and C % 4 != 0 and stride > 1):
         return None
     S = stride
-    Hs, Ws = -(-H // S), -(-W // S)
+    Hp, Wp = H + 2 * pad, W + 2 * pad
+    Hs, Ws = -(-Hp // S), -(-Wp // S)
     KHs, KWs = -(-KH // S), -(-KW // S)
     Ho, Wo = _out_hw(H, W, KH, KW, stride, pad)
     if Hs - KHs + 1 != Ho or Ws - KWs + 1 != Wo:
         return None
     Cp = (S * S * C + 7) // 8 * 8
-    return S, Hs, Ws, KHs, KWs, Cp, Ho, Wo
+    return S, Hs, Ws, KHs, KWs, Cp, Ho, Wo, int(pad)
 
 
 def _conv_s2d_fwd(x, w, b, relu, g):
     """First-layer conv (e.g. AlexNet 11x11/4 on RGB) as a stride-1 conv on the space-to-depth image (implicit GEMM)."""
-    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo = g
+    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo, P0 = g
     N, H, W, C = x.shape
     O, KH, KW, _ = w.shape
     dev = x.device
@@ -295,10 +297,10 @@ def _conv_s2d_fwd(x, w, b, relu, g):
     xs = torch.empty((N, Hs, Ws, Cp), dtype=x.dtype, device=dev)
     ws = torch.empty((O, KHs, KWs, Cp), dtype=x.dtype, device=dev)
     if f32:
-        L().space_to_depth_f32(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
+        L().space_to_depth_f32(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, P0, _st(x))
         L().s2d_filter_pack_f32(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, _st(x))
     else:
-        L().space_to_depth(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, _st(x))
+        L().space_to_depth(x.data_ptr(), xs.data_ptr(), N, H, W, C, S, Hs, Ws, Cp, P0, _st(x))
         L().s2d_filter(_bf(w).contiguous().data_ptr(), ws.data_ptr(), O, KH, KW, C, S, KHs, KWs, Cp, 0, _st(x))
     y = torch.empty((N, Ho, Wo, O), dtype=x.dtype, device=dev)
     L().conv_fprop(xs.data_ptr(), ws.data_ptr(), y.data_ptr(), _p(b), N, Hs, Ws, Cp, 0, Cp, KHs, KWs, Ho, Wo, 1, 0, O, O,
@@ -307,7 +309,7 @@ def _conv_s2d_fwd(x, w, b, relu, g):
 
 
 def _conv_s2d_bwd(xs, w, y, dy, relu, g, dw_out, db_out, pre_masked=False):
-    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo = g
+    S, Hs, Ws, KHs, KWs, Cp, Ho, Wo, P0 = g
     O, KH, KW, C = w.shape
     N = xs.shape[0]
     M = N * Ho * Wo

@@ -85,6 +85,12 @@ class BSP_Exchanger(object):
             if gpucomm is None:
                 raise RuntimeError("strategy %s needs the symmetric peer arena (GPUs of one node)" % exch_strategy)
             self.algo, self.wire16 = FUSED[exch_strategy]
+            # owner-keeps-master (default when the model computes from bf16 shadows): the fused kernel ships only the bf16
+            # compute shadow of an updated slice to the peers — a third of the all-gather bytes; the fp32 master copies of
+            # non-owners go stale until sync_master() (called before checkpoints / by finalize).  TMPI_PUSH_MASTER=1 restores
+            # the full push.
+            self.push_master = (os.environ.get("TMPI_PUSH_MASTER", "0") == "1") or self.arena.H is None
+            self._master_stale = False
             self._setup_buckets()
             return
         if sync_type == "cdd":
@@ -180,7 +186,23 @@ class BSP_Exchanger(object):
             big = int(os.environ.get("TMPI_OVERLAP_BLOCKS", "64"))     # measured at 2 ranks: 16 → 4.5 ms, 32 → 3.1, 64 → 2.17, 148 → 2.28
             blocks = big if (b["hi"] - b["lo"]) * 4 > (8 << 20) else min(8, big)
         self.gpucomm.fused_allreduce_sgd(self.arena, b["lo"], b["hi"], mu, m.use_nesterov_momentum,
-                                         algo=self.algo, wire16=self.wire16, max_blocks=blocks, pre_reduced=b.get("rs", False))
+                                         algo=self.algo, wire16=self.wire16, max_blocks=blocks, pre_reduced=b.get("rs", False),
+                                         push_master=self.push_master)
+        if not self.push_master:
+            self._master_stale = True
+
+    def sync_master(self):
+        """Collective: make every rank's fp32 master weights current again (owner-keeps-master mode).  Buckets that ran the
+        one-shot algorithm are already identical everywhere; the two-shot ones push their owner slices."""
+        if not getattr(self, "fused", False) or self.push_master or not self._master_stale:
+            return
+        for b in self.buckets:
+            nbytes = (b["hi"] - b["lo"]) * (2 if self.wire16 else 4)
+            if self.gpucomm.pick_algo(nbytes, self.algo) != 0 or b.get("rs", False):
+                self.gpucomm.push_master_slices(self.arena, b["lo"], b["hi"])
+        torch.cuda.synchronize(self.arena.device)
+        self.comm.Barrier()
+        self._master_stale = False
 
     def _on_ready(self, p):
         """Called by a backward kernel wrapper right after it enqueued the gradient of ``p``."""

@@ -190,7 +190,7 @@ class SymmetricComm(object):
         return ALGO["nvls"] if self.has_multicast else ALGO["twoshot"]
 
     def fused_allreduce_sgd(self, arena, lo, hi, mu, nesterov, inv_k=None, algo="auto", wire16=False, max_blocks=None,
-                            pre_reduced=False):
+                            pre_reduced=False, push_master=True):
         """``pre_reduced``: the range's gradients were already reduce-scattered into their owner's G by the wgrad GEMM
         epilogues (``configure_gemm_rs`` / ``gemm_rs_add_range``) — the kernel skips the gather, updates its slice, pushes
         W / H and clears G."""
@@ -204,8 +204,16 @@ class SymmetricComm(object):
                                     arena.block_group.data_ptr(), lrm, wd, ex, arena.hyper.data_ptr(), float(mu),
                                     int(bool(nesterov)), float(inv_k if inv_k is not None else 1.0 / self.size),
                                     int(lo), int(hi), int(bool(wire16)), a, self._blocks(max_blocks), self._stream(),
-                                    int(bool(pre_reduced)))
+                                    int(bool(pre_reduced)), int(bool(push_master)))
         return a
+
+    def push_master_slices(self, arena, lo, hi, max_blocks=None):
+        """All ranks: push the fp32 master weights of the slice each rank owns in the two-shot partition of ``[lo, hi)`` to the
+        peers (re-synchronises ``W`` after fused steps that ran with ``push_master=False``)."""
+        from ..ops.cuda_impl import _table
+        lrm, wd, ex = _table(arena)
+        self.pa.push_master_slices(arena.layout["W"], arena.block_group.data_ptr(), lrm, wd, ex, int(lo), int(hi),
+                                   self._blocks(max_blocks), self._stream())
 
     def configure_gemm_rs(self, arena, ranges):
         """Arm the reduce-scatter epilogue of the GEMM for the given single-tensor buckets ``[(lo, hi), …]`` (element ranges

@@ -143,8 +143,11 @@ class BSP_Worker(MPI_GPU_Process):
             # lr schedule BEFORE the snapshot: ckpt_<epoch> must carry the lr epoch+1 will train with (every lr_step of the
             # zoo is a multiple of snapshot_freq — saving first would lose that decay on resume)
             model.adjust_hyperp(epoch)
-            if epoch % snapshot_freq == 0 and self.rank == 0:
-                save_model(model, snapshot_path, verbose=self.verbose, recorder=recorder)
+            if epoch % snapshot_freq == 0:
+                if hasattr(exchanger, "sync_master"):
+                    exchanger.sync_master()               # owner-keeps-master: rank 0 is about to read every fp32 weight
+                if self.rank == 0:
+                    save_model(model, snapshot_path, verbose=self.verbose, recorder=recorder)
             # rank 0 may have spent seconds writing files: park everybody on the HOST here — the next fused step spins in a
             # device-side flag barrier, which is the wrong place to wait for a slow disk
             self.comm.Barrier()
@@ -153,6 +156,8 @@ class BSP_Worker(MPI_GPU_Process):
             recorder.end_epoch(batch_i * self.size, epoch)
             if self.stop:
                 break
+        if hasattr(exchanger, "sync_master"):
+            exchanger.sync_master()
         model.cleanup()
 
 

@@ -123,7 +123,7 @@ void s2d_filter_pack_f32(const void* src, void* dst, int O, int KH, int KW, int 
 void bn_forward(const void* x, const void* res, void* y, const void* gamma, const void* beta, void* mean, void* rstd, void* run_mean,
                 void* run_var, void* scratch, long long R, int C, float momentum, float eps, int training, int relu, int f32, cudaStream_t st);
 void bn_backward(const void* x, const void* dy, const void* y, void* dx, void* dres, const void* gamma, const void* mean, const void* rstd,
-                 void* dgamma, void* dbeta, long long R, int C, int relu, int f32, cudaStream_t st);
+                 void* dgamma, void* dbeta, void* scratch, long long R, int C, int relu, int f32, cudaStream_t st);
 void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cudaStream_t st);
 void add4_tensors(const void* a, const void* b, const void* c, const void* d, void* y, long long n, int f32, cudaStream_t st);
 

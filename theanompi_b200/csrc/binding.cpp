@@ -162,8 +162,8 @@ PYBIND11_MODULE(_tmpi_native, m) {
     bn_forward(P(x), P(res), P(y), P(gamma), P(beta), P(mean), P(rstd), P(run_mean), P(run_var), P(scratch), R, C, momentum, eps, training, relu,
                f32, S(st)); });
   m.def("bn_backward", [](ptr_t x, ptr_t dy, ptr_t y, ptr_t dx, ptr_t dres, ptr_t gamma, ptr_t mean, ptr_t rstd, ptr_t dgamma, ptr_t dbeta,
-                          long long R, int C, int relu, int f32, ptr_t st) {
-    bn_backward(P(x), P(dy), P(y), P(dx), P(dres), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), R, C, relu, f32, S(st)); });
+                          ptr_t scratch, long long R, int C, int relu, int f32, ptr_t st) {
+    bn_backward(P(x), P(dy), P(y), P(dx), P(dres), P(gamma), P(mean), P(rstd), P(dgamma), P(dbeta), P(scratch), R, C, relu, f32, S(st)); });
   m.def("add4_tensors", [](ptr_t a, ptr_t b, ptr_t c, ptr_t d, ptr_t y, long long n, int f32, ptr_t st) {
     add4_tensors(P(a), P(b), P(c), P(d), P(y), n, f32, S(st)); });
   m.def("add_tensors", [](ptr_t a, ptr_t b, ptr_t y, long long n, int f32, ptr_t st) { add_tensors(P(a), P(b), P(y), n, f32, S(st)); });

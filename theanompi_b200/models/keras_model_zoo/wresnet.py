@@ -129,8 +129,12 @@ class Wide_ResNet(ModelBase):
         x = ((x.float() - self._mean) / 64.0).to(self.act_dtype)
         x = self.stem.forward(x)
         for bn1, short, c1, bn2, c2 in self.body:                 # pre-activation block (ref :37-82)
-            o = bn1.forward(x)
-            s = x if short is None else short.forward(o)
+            if short is None:
+                x, s = ops.fork2(x)                               # identity shortcut: x feeds bn1 and the merge
+                o = bn1.forward(x)
+            else:
+                o, o2 = ops.fork2(bn1.forward(x))                 # projection shortcut reads the pre-activated tensor
+                s = short.forward(o2)
             o = c2.forward(bn2.forward(c1.forward(o)))
             x = ops.add(o, s)
         bn, gap, flat, sm = self.head

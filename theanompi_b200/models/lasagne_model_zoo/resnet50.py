@@ -146,8 +146,10 @@ class ResNet50(ModelBase):
     def forward(self, x):
         c, b, pool = self.stem
         x = pool.forward(b.forward(c.forward(x)))
+        from ... import ops
         for c1, b1, c2, b2, c3, b3, proj in self.body:
-            short = x if proj is None else proj[1].forward(proj[0].forward(x))
+            x, xs = ops.fork2(x)                                  # two consumers: the branch and the shortcut
+            short = xs if proj is None else proj[1].forward(proj[0].forward(xs))
             y = b1.forward(c1.forward(x))
             y = b2.forward(c2.forward(y))
             x = b3.forward(c3.forward(y), residual=short)         # relu(bn(conv) + shortcut) in one kernel

@@ -588,8 +588,10 @@ def batch_norm_bwd(x, dy, y, gamma, mean, rstd, relu, need_dres, dgamma_out=None
     dres = torch.empty_like(x) if (need_dres and relu) else None
     dgamma = dgamma_out.view(-1) if dgamma_out is not None else torch.empty(C, dtype=F32, device=dev)
     dbeta = dbeta_out.view(-1) if dbeta_out is not None else torch.empty(C, dtype=F32, device=dev)
+    scratch = torch.empty(3 * C, dtype=F32, device=dev)
     L().bn_backward(x.data_ptr(), dy.data_ptr(), _p(y) if relu else 0, dx.data_ptr(), _p(dres), gamma.data_ptr(), mean.data_ptr(),
-                    rstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), int(R), int(C), int(bool(relu)), int(_is32(x)), _st(x))
+                    rstd.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), scratch.data_ptr(), int(R), int(C), int(bool(relu)),
+                    int(_is32(x)), _st(x))
     if need_dres and not relu:
         dres = dy
     return dx, dres, dgamma, dbeta

@@ -309,6 +309,33 @@ class _AddFn(torch.autograd.Function):
         return dy, dy
 
 
+class _Fork2Fn(torch.autograd.Function):
+    """Fan-out of a tensor to two consumers: the two incoming gradients are summed by the native add kernel (autograd would
+    otherwise accumulate them with a library elementwise kernel)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, d1, d2):
+        if d1 is None:
+            return d2
+        if d2 is None:
+            return d1
+        if d1.is_cuda:
+            from . import cuda_impl
+            return cuda_impl.add(d1, d2)
+        return d1 + d2
+
+
+def fork2(x):
+    """Return two aliases of ``x`` for two consumers (residual shortcut + branch)."""
+    if not x.requires_grad:
+        return x, x
+    return _Fork2Fn.apply(x)
+
+
 def add(a, b):
     """Residual merge ``a + b`` (native kernel on CUDA; the gradient passes to both branches unchanged)."""
     return _AddFn.apply(a, b)

@@ -115,7 +115,8 @@ def test_gans_and_lstm():
     _run("theanompi_b200.models.lasagne_model_zoo.wgan", "WGAN", dict(critic_runs=2, data_kwargs=dict(n_synthetic=256)), steps=2)
     _run("theanompi_b200.models.lasagne_model_zoo.lsgan", "LSGAN", dict(data_kwargs=dict(n_synthetic=256)), steps=2)
     _run("theanompi_b200.models.lasagne_model_zoo.lsgan_cifar10", "LSGAN", dict(data_kwargs=dict(n_synthetic=256, synthetic=True)), steps=2)
-    _run("theanompi_b200.models.lstm", "LSTM", dict(dim_proj=32, data_kwargs=dict(n_synthetic=128, n_words=500)), steps=3)
+    _run("theanompi_b200.models.lstm", "LSTM", dict(dim_proj=64, data_kwargs=dict(n_synthetic=128, n_words=500)), steps=3)
+    _run("theanompi_b200.models.lstm", "LSTMTorch", dict(dim_proj=32, data_kwargs=dict(n_synthetic=128, n_words=500)), steps=3)
 
 
 def test_loader_pipeline_matches_reference_crop():

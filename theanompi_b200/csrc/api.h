@@ -127,6 +127,16 @@ void bn_backward(const void* x, const void* dy, const void* y, void* dx, void* d
 void add_tensors(const void* a, const void* b, void* y, long long n, int f32, cudaStream_t st);
 void add4_tensors(const void* a, const void* b, const void* c, const void* d, void* y, long long n, int f32, cudaStream_t st);
 
+// ---- rnn_kernels.cu: LSTM cell fwd / bwd, embedding gather / scatter, masked mean pooling  (f32: fp32 activations, else bf16)
+void lstm_cell_fwd(const void* gx, const void* gh, const void* c_prev, const void* h_prev, const void* mask, void* act, void* c_out, void* h_out,
+                   int B, int H, int f32, cudaStream_t st);
+void lstm_cell_bwd(const void* dh_out, const void* dh_rec, const void* dh_pass_in, const void* dc_next, const void* act, const void* c,
+                   const void* c_prev, const void* mask, void* dG, void* dc_prev, void* dh_pass, int B, int H, int f32, cudaStream_t st);
+void embedding_fwd(const void* ids, const void* W, void* out, long long n, int D, int f32, cudaStream_t st);
+void embedding_bwd(const void* ids, const void* dout, void* dW, long long n, int D, long long V, int f32, cudaStream_t st);
+void masked_mean_fwd(const void* h, const void* mask, void* out, int Tn, int B, int H, int f32, cudaStream_t st);
+void masked_mean_bwd(const void* dout, const void* mask, void* dh, int Tn, int B, int H, int f32, cudaStream_t st);
+
 // ---- comm_kernels.cu
 void sgd_flat(void* W, const void* G, void* U, void* H, const void* block_group, const GroupTable& tab, const void* lr_ptr, float mu,
               int nesterov, float inv_k, long long lo, long long hi, int filter, cudaStream_t st);

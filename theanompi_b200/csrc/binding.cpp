@@ -168,6 +168,18 @@ PYBIND11_MODULE(_tmpi_native, m) {
     add4_tensors(P(a), P(b), P(c), P(d), P(y), n, f32, S(st)); });
   m.def("add_tensors", [](ptr_t a, ptr_t b, ptr_t y, long long n, int f32, ptr_t st) { add_tensors(P(a), P(b), P(y), n, f32, S(st)); });
 
+  // ---------------------------------------------------------------- recurrent / embedding
+  m.def("lstm_cell_fwd", [](ptr_t gx, ptr_t gh, ptr_t c_prev, ptr_t h_prev, ptr_t mask, ptr_t act, ptr_t c_out, ptr_t h_out, int B, int H, int f32,
+                            ptr_t st) { lstm_cell_fwd(P(gx), P(gh), P(c_prev), P(h_prev), P(mask), P(act), P(c_out), P(h_out), B, H, f32, S(st)); });
+  m.def("lstm_cell_bwd", [](ptr_t dh_out, ptr_t dh_rec, ptr_t dh_pass_in, ptr_t dc_next, ptr_t act, ptr_t c, ptr_t c_prev, ptr_t mask, ptr_t dG,
+                            ptr_t dc_prev, ptr_t dh_pass, int B, int H, int f32, ptr_t st) {
+    lstm_cell_bwd(P(dh_out), P(dh_rec), P(dh_pass_in), P(dc_next), P(act), P(c), P(c_prev), P(mask), P(dG), P(dc_prev), P(dh_pass), B, H, f32, S(st)); });
+  m.def("embedding_fwd", [](ptr_t ids, ptr_t W, ptr_t out, long long n, int D, int f32, ptr_t st) { embedding_fwd(P(ids), P(W), P(out), n, D, f32, S(st)); });
+  m.def("embedding_bwd", [](ptr_t ids, ptr_t dout, ptr_t dW, long long n, int D, long long V, int f32, ptr_t st) {
+    embedding_bwd(P(ids), P(dout), P(dW), n, D, V, f32, S(st)); });
+  m.def("masked_mean_fwd", [](ptr_t h, ptr_t mask, ptr_t out, int Tn, int B, int H, int f32, ptr_t st) { masked_mean_fwd(P(h), P(mask), P(out), Tn, B, H, f32, S(st)); });
+  m.def("masked_mean_bwd", [](ptr_t dout, ptr_t mask, ptr_t dh, int Tn, int B, int H, int f32, ptr_t st) { masked_mean_bwd(P(dout), P(mask), P(dh), Tn, B, H, f32, S(st)); });
+
   // ---------------------------------------------------------------- optimizer / legacy kernels
   m.def("sgd_flat", [](ptr_t W, ptr_t G, ptr_t U, ptr_t H, ptr_t block_group, std::vector<float> lr_mult, std::vector<float> wd,
                        std::vector<int> exch, ptr_t lr_ptr, float mu, int nesterov, float inv_k, long long lo, long long hi, int filter,

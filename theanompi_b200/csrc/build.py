@@ -28,7 +28,7 @@ SO_PATH = os.path.join(PKG, "_tmpi_native.so")
 OBJ_DIR = os.path.join(HERE, "_obj")
 STAMP = os.path.join(PKG, "_tmpi_native.hash")
 
-CU_SOURCES = ["gemm_tcgen05.cu", "nn_kernels.cu", "nn_kernels_f32.cu", "bn_kernels.cu", "comm_kernels.cu"]
+CU_SOURCES = ["gemm_tcgen05.cu", "nn_kernels.cu", "nn_kernels_f32.cu", "bn_kernels.cu", "rnn_kernels.cu", "comm_kernels.cu"]
 CPP_SOURCES = ["peer_arena.cpp", "binding.cpp"]
 HEADERS = ["common.cuh", "api.h", "peer_arena.h"]
 

@@ -366,8 +366,15 @@ void fused_allreduce_sgd(const FusedArgs& a, int algo, int max_blocks, cudaStrea
   } else {
     const long long per = (nb + a.ctx.world - 1) / a.ctx.world;
     const int nv = algo == 2 ? 1 : 0;
-    if (wide && !nv) fused_twoshot_sgd_kernel<2><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
-    else fused_twoshot_sgd_kernel<4><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
+    // loads in flight per thread = U (NVLS: one multimem.ld_reduce per block) or U x world (P2P gather).  The exchange runs
+    // next to the backward GEMMs on a few dozen co-resident CTAs, so its throughput is (bytes in flight) / (NVLink round trip):
+    // keep 8..16 independent 16-byte loads per thread outstanding.  TMPI_FUSED_U overrides (2, 4 or 8).
+    static const int u_env = [] { const char* e = getenv("TMPI_FUSED_U"); return e ? atoi(e) : 0; }();
+    int U = nv ? 8 : (a.ctx.world <= 2 ? 8 : (wide ? 2 : 4));
+    if (u_env == 2 || u_env == 4 || u_env == 8) U = u_env;
+    if (U == 8) fused_twoshot_sgd_kernel<8><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
+    else if (U == 4) fused_twoshot_sgd_kernel<4><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
+    else fused_twoshot_sgd_kernel<2><<<pick_grid(per, max_blocks), kThreads, 0, st>>>(a, nv);
   }
   count_launch(); TMPI_CHECK_LAUNCH("fused_allreduce_sgd"); ::tmpi::check_capture(st, "fused_allreduce_sgd");
 }

@@ -160,3 +160,31 @@ def test_loader_process_mode_gpu(tmp_path, monkeypatch):
             assert np.abs(b.x.float().cpu().numpy() - want).max() < 4e-3, i
     finally:
         ld.close()
+
+
+def test_deterministic_mode_is_bit_reproducible():
+    """TMPI_DETERMINISTIC=1 (no split-K: every gradient element is produced by one CTA in a fixed k order) → two runs of the same
+    training steps give bit-identical weights; the default (split-K with fp32 atomics in arrival order) is only close."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import torch, sys\n"
+        "from theanompi_b200.models import layers2\n"
+        "from theanompi_b200.models.cifar10 import Cifar10_model\n"
+        "from theanompi_b200.utils.recorder import Recorder\n"
+        "m = Cifar10_model(dict(verbose=False, rank=0, size=1, device='cuda:0', batch_size=64, file_batch_size=64, cuda_graph=False,\n"
+        "                       data_kwargs=dict(n_synthetic=512, synthetic=True)))\n"
+        "layers2.Dropout.SetDropoutOff(); layers2.Crop.SetRandCropOff()\n"
+        "m.compile_iter_fns('avg'); rec = Recorder(None, 10**6, 'c', False, device='cuda:0')\n"
+        "for i in range(4): m.train_iter(i, rec)\n"
+        "torch.cuda.synchronize(); torch.save(m.arena.W.cpu(), sys.argv[1])\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for k in range(2):
+        f = "/tmp/tmpi_det_%d.pt" % k
+        env = dict(os.environ, TMPI_DETERMINISTIC="1", PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code, f], env=env, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:]
+        outs.append(torch.load(f))
+    assert torch.equal(outs[0], outs[1])

@@ -55,23 +55,36 @@ __global__ void __launch_bounds__(256) bn_colreduce_kernel(const T* __restrict__
       for (int i = 0; i < N; ++i) { mu[i] = mean[cv * N + i]; rs[i] = rstd[cv * N + i]; }
     }
     const long long rend = min(R, r0 + rows_per_cta);
-    for (long long r = r0 + tr; r < rend; r += RL) {
-      float xv[N];
-      VecIO<T>::ld(x + r * C + cv * N, xv);
-      if (MODE == 0) {
+    // 4 rows per trip, all loads issued before any use (this pass is pure streaming: memory-level parallelism is everything)
+    for (long long r = r0 + tr; r < rend; r += 4 * RL) {
+      float xv[4][N], gv[4][N], yv[4][N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] += xv[i]; b[i] += xv[i] * xv[i]; }
-      } else {
-        float g[N];
-        VecIO<T>::ld(dy + r * C + cv * N, g);
-        if (relu) {
-          float yv[N];
-          VecIO<T>::ld(y + r * C + cv * N, yv);
-#pragma unroll
-          for (int i = 0; i < N; ++i) if (!(yv[i] > 0.f)) g[i] = 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * RL;
+        if (rr < rend) {
+          VecIO<T>::ld(x + rr * C + cv * N, xv[u]);
+          if (MODE == 1) {
+            VecIO<T>::ld(dy + rr * C + cv * N, gv[u]);
+            if (relu) VecIO<T>::ld(y + rr * C + cv * N, yv[u]);
+          }
         }
+      }
 #pragma unroll
-        for (int i = 0; i < N; ++i) { a[i] += g[i]; b[i] += g[i] * (xv[i] - mu[i]) * rs[i]; }
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + (long long)u * RL;
+        if (rr < rend) {
+          if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) { a[i] += xv[u][i]; b[i] += xv[u][i] * xv[u][i]; }
+          } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              float g = gv[u][i];
+              if (relu && !(yv[u][i] > 0.f)) g = 0.f;
+              a[i] += g; b[i] += g * (xv[u][i] - mu[i]) * rs[i];
+            }
+          }
+        }
       }
     }
   }
@@ -104,6 +117,7 @@ static void colreduce(const void* x, const void* dy, const void* y, const float*
   const int RL = 256 / VT;
   // enough CTAs to fill the machine a few times, few enough that the atomics stay cheap
   long long slabs = std::max<long long>(1, std::min<long long>((R + RL - 1) / RL, (long long)sm_count() * 8 / std::max(1, (nvec + VT - 1) / VT)));
+  if (deterministic_mode()) slabs = 1;                     // one CTA per channel group: fixed summation order, no atomics race
   const int rows_per_cta = (int)((R + slabs - 1) / slabs);
   dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)2 * RL * VT * N * sizeof(float);

@@ -75,6 +75,14 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 #endif
 
+// TMPI_DETERMINISTIC=1: bit-reproducible training steps — no split-K (gradient tiles are otherwise combined with fp32 atomics in
+// arrival order) and every cross-CTA atomic reduction (bias gradients, batch-norm statistics) collapses to one CTA per channel
+// group with a fixed summation order.  Slower; meant for debugging / regression runs.
+inline bool deterministic_mode() {
+  static const bool v = [] { const char* e = getenv("TMPI_DETERMINISTIC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 inline int sm_count() {
   static int n = 0;
   if (n == 0) {

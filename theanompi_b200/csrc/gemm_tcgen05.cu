@@ -785,6 +785,9 @@ static int bulk_default() {
 // waves x (k-blocks per slice + per-tile overhead).  A plain ceil(sms / tiles) overshoots the machine by a few tiles
 // and pays a whole second wave for them (conv2 wgrad: 13 tiles x 12 slices = 156 > 148).
 static int choose_splits(int tiles, int num_kb, int sms) {
+  // TMPI_DETERMINISTIC=1: never split K — split-K slices combine with fp32 red.global.add in arrival order, so weight gradients
+  // differ in the last bits from run to run; without it every output element is produced by ONE CTA in a fixed k order
+  if (deterministic_mode()) return 1;
   if (tiles >= sms || num_kb < 8) return 1;
   const int kTileOverheadKb = 4;                    // pipeline fill + accumulator hand-off, in k-block units
   int best = 1;

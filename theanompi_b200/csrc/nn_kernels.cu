@@ -533,7 +533,10 @@ void relu_bias_bwd2(const void* dy, const void* y, void* dym, void* db, void* db
   const int nvec = C / 8;
   const int VT = nvec < 32 ? nvec : 32;
   const int RL = 256 / VT;
-  const int rows_per_cta = RL * 8;
+  // deterministic mode: one CTA per channel group sums ALL rows (fixed order) instead of row slabs + atomics
+  const long long rows_per_cta_ll = deterministic_mode() ? std::max<long long>(R, 1) : (long long)RL * 8;
+  if (rows_per_cta_ll >= (1LL << 31)) throw std::runtime_error("relu_bias_bwd: too many rows for the deterministic mode");
+  const int rows_per_cta = (int)rows_per_cta_ll;
   dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)RL * VT * 8 * sizeof(float);
   if (!db1 || c_split > C) c_split = C;

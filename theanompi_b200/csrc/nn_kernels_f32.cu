@@ -294,7 +294,7 @@ void relu_bias_bwd2_f32(const void* dy, const void* y, void* dym, void* db, void
   const int nvec = C / 4;
   const int VT = nvec < 32 ? nvec : 32;
   const int RL = 256 / VT;
-  const int rows_per_cta = RL * 8;
+  const int rows_per_cta = deterministic_mode() ? (int)std::max<long long>(R, 1) : RL * 8;
   dim3 grid((unsigned)((R + rows_per_cta - 1) / rows_per_cta), (unsigned)((nvec + VT - 1) / VT));
   const size_t smem = (size_t)RL * VT * 4 * sizeof(float);
   if (!db1 || c_split > C) c_split = C;

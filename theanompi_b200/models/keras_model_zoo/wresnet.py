@@ -126,7 +126,15 @@ class Wide_ResNet(ModelBase):
 
     def forward(self, x):
         from ... import ops
-        x = ((x.float() - self._mean) / 64.0).to(self.act_dtype)
+        if x.is_cuda:
+            # (x − mean) / 64 → activation dtype in ONE native kernel (the loader's normalise kernel with a full-image crop)
+            if getattr(self, "_zero_off", None) is None or self._zero_off.shape[0] != x.shape[0]:
+                self._zero_off = torch.zeros((x.shape[0], 2), dtype=torch.int32, device=x.device)
+                self._zero_flip = torch.zeros((x.shape[0],), dtype=torch.uint8, device=x.device)
+            x = ops.crop_mirror_normalize(x.float() if x.dtype not in (torch.float32, torch.bfloat16, torch.uint8) else x, self._mean,
+                                          1.0 / 64.0, (x.shape[1], x.shape[2]), self._zero_off, self._zero_flip, out_dtype=self.act_dtype)
+        else:
+            x = ((x.float() - self._mean) / 64.0).to(self.act_dtype)
         x = self.stem.forward(x)
         for bn1, short, c1, bn2, c2 in self.body:                 # pre-activation block (ref :37-82)
             if short is None:

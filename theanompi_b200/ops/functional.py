@@ -100,7 +100,9 @@ def _fused_pool_ok(x, relu, pool):
     """conv(+ReLU) → max-pool blocks run their backward through ONE fused kernel (pool scatter + ReLU mask + bias grad)."""
     # (bf16 path only: the fused kernel works on packed bf16 lanes; the fp32 / tf32 path runs pool-backward and ReLU-mask +
     # bias-gradient as two kernels)
-    return pool is not None and x.is_cuda and relu and pool[3] == "max" and x.dtype == torch.bfloat16
+    # TMPI_DETERMINISTIC=1 also takes the two-kernel route: the fused kernel reduces the bias gradient with cross-CTA atomics
+    return (pool is not None and x.is_cuda and relu and pool[3] == "max" and x.dtype == torch.bfloat16
+            and os.environ.get("TMPI_DETERMINISTIC") != "1")
 
 
 def _pool_fwd_after(ctx, impl, y, pool):

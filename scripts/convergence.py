@@ -5,7 +5,7 @@
                                                                      global batch fixed at 128: per-GPU batch 128 / N
 
 Model: Cifar10_model on the synthetic class-separable CIFAR-shaped set (no dataset in this environment).  Prints one JSON line
-with the smoothed training loss every 20 steps vs images seen, and the final validation error.
+with (images seen, smoothed training loss, validation cost, validation error) every 20 steps.
 """
 import argparse
 import json
@@ -35,19 +35,22 @@ def run_one(dtype, steps, rank, size, batch, worker=None, lr=0.001):
         m.compile_iter_fns("avg")
         rec, exch = Recorder(None, 10 ** 6, "c", False, device=dev), None
     curve = []
+    verr = None
     for i in range(steps):
         m.train_iter(i, rec)
         if exch is not None:
             exch.exchange(rec)
         if (i + 1) % 20 == 0:
             loss = float(torch.stack([c.float() for c in rec.train_info["cost"][-20:]]).mean())
-            curve.append((int((i + 1) * batch * size), round(loss, 4)))
-    layers2.Dropout.SetDropoutOff(); layers2.Crop.SetRandCropOff()
-    errs = []
-    for j in range(min(4, m.data.n_batch_val)):
-        m.val_iter(j, rec)
-    verr = float(torch.stack([torch.as_tensor(e).float() for e in rec.val_info["error"][-4:]]).mean()) if hasattr(rec, "val_info") else None
-    layers2.Dropout.SetDropoutOn(); layers2.Crop.SetRandCropOn()
+            # validation cost / error of the current weights (eval mode: no dropout, centre crop) on the first val batches —
+            # the smooth curve the reference plots (README.md:122-123)
+            n0 = len(rec.val_info["cost"])
+            for j in range(min(2, m.data.n_batch_val)):
+                m.val_iter(j, rec)
+            m.reset_iter("val")
+            vc = float(torch.stack([torch.as_tensor(c).float() for c in rec.val_info["cost"][n0:]]).mean())
+            verr = float(torch.stack([torch.as_tensor(e).float() for e in rec.val_info["error"][n0:]]).mean())
+            curve.append((int((i + 1) * batch * size), round(loss, 4), round(vc, 4), round(verr, 4)))
     m.cleanup()
     return curve, verr
 
@@ -73,8 +76,8 @@ def main():
     for dt in ("bf16", "tf32"):
         curve, verr = run_one(dt, a.steps, 0, 1, a.global_batch)
         out[dt] = {"curve": curve, "val_err": verr}
-    d = max(abs(x[1] - y[1]) for x, y in zip(out["bf16"]["curve"], out["tf32"]["curve"]))
-    out["max_abs_loss_gap_bf16_vs_tf32"] = d
+    out["max_abs_train_loss_gap_bf16_vs_tf32"] = max(abs(x[1] - y[1]) for x, y in zip(out["bf16"]["curve"], out["tf32"]["curve"]))
+    out["max_abs_val_cost_gap_bf16_vs_tf32"] = max(abs(x[2] - y[2]) for x, y in zip(out["bf16"]["curve"], out["tf32"]["curve"]))
     print("CONVERGENCE " + json.dumps(out), flush=True)
 
 

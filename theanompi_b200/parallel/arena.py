@@ -200,7 +200,7 @@ class FlatArena(object):
         return self._ex_vec
 
     # ------------------------------------------------------------------ buckets (reverse layer order for overlap)
-    def make_buckets(self, bucket_bytes, solo=()):
+    def make_buckets(self, bucket_bytes, solo=(), tail_bytes=0):
         """Split the arena into contiguous block ranges.  Bucket 0 holds the LAST
         parameters (their gradients are ready first in backward).  Parameters listed in
         ``solo`` always get a bucket of their own."""
@@ -218,6 +218,21 @@ class FlatArena(object):
             buckets.append({"lo": lo, "hi": hi, "params": members[::-1]})
             hi = lo
             i -= 1
+        # The LAST bucket (the first layers) becomes ready only when backward ends: whatever it exchanges is exposed.  Split it so
+        # that only a small tail (<= tail_bytes) waits for the very last gradients; the rest starts as soon as its own layers
+        # are done.
+        if tail_bytes and buckets and len(buckets[-1]["params"]) > 1 and not (set(buckets[-1]["params"]) & set(solo)):
+            b = buckets[-1]
+            tail_target = max(BLOCK, int(tail_bytes) // 4)
+            if b["hi"] - b["lo"] > 2 * tail_target:
+                ps = b["params"]
+                k = 1
+                while k < len(ps) - 1 and self.offsets[ps[k + 1]] - b["lo"] <= tail_target:
+                    k += 1
+                cut = self.offsets[ps[k]]
+                if b["lo"] < cut < b["hi"]:
+                    buckets[-1] = {"lo": cut, "hi": b["hi"], "params": ps[k:]}
+                    buckets.append({"lo": b["lo"], "hi": cut, "params": ps[:k]})
         return buckets
 
     # ------------------------------------------------------------------ checkpoint

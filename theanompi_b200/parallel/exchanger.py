@@ -159,7 +159,8 @@ class BSP_Exchanger(object):
             torch.cuda.synchronize(a.device)
             self.comm.Barrier()
         else:
-            self.buckets = a.make_buckets(bb) if self.overlap else [dict(lo=0, hi=a.numel, params=list(range(len(a.params))))]
+            tail = int(os.environ.get("TMPI_TAIL_BUCKET_BYTES", str(4 << 20)))
+            self.buckets = a.make_buckets(bb, tail_bytes=tail) if self.overlap else [dict(lo=0, hi=a.numel, params=list(range(len(a.params))))]
         self._pending = [0] * len(self.buckets)
         self._bucket_of = {}
         for bi, b in enumerate(self.buckets):

@@ -60,15 +60,17 @@ def main():
     ap.add_argument("--steps", type=int, default=320)
     ap.add_argument("--bsp", action="store_true")
     ap.add_argument("--global-batch", type=int, default=128)
+    ap.add_argument("--strategy", default="fused")
     a = ap.parse_args()
     rank, size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
     out = {"steps": a.steps, "n_gpus": size, "global_batch": a.global_batch}
     if a.bsp or size > 1:
         from theanompi_b200.worker import BSP_Worker
-        w = BSP_Worker("cuda%d" % int(os.environ.get("LOCAL_RANK", "0")), "cdd", "fused")
+        w = BSP_Worker("cuda%d" % int(os.environ.get("LOCAL_RANK", "0")), "cdd", a.strategy)
         curve, verr = run_one("bf16", a.steps, rank, size, a.global_batch // size, worker=w if size > 1 else None)
-        out["bsp_bf16"] = {"curve": curve, "val_err": verr}
+        out["bsp_bf16"] = {"curve": curve, "val_err": verr, "strategy": a.strategy, "push_master": os.environ.get("TMPI_PUSH_MASTER", "0"),
+                           "nvls": os.environ.get("TMPI_NVLS", "1")}
         if rank == 0:
             print("CONVERGENCE " + json.dumps(out), flush=True)
         w.finalize()

@@ -77,3 +77,25 @@ def test_rule_gosgd_gpu(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     n = min(4, torch.cuda.device_count())
     assert _run_rule(tm.GOSGD, ["cuda%d" % i for i in range(n)], cfg=dict(gosgd_p=0.3)) == 0
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_fused_exchange_follows_classic_trajectory():
+    """Training curves of the default fused exchange (owner-keeps-master, NVLS or P2P) and of the classic per-tensor NCCL
+    strategy coincide (same data, same init): the reference's "1/2/4/8-GPU curves coincide" property, and a guard against
+    any rank computing with stale parameters."""
+    import json
+    curves = {}
+    for name, strat, env in (("classic", "nccl32", {}), ("fused", "fused", {}), ("fused_p2p", "fused", {"TMPI_NVLS": "0"})):
+        e = dict(os.environ); e.update(env)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29640", os.path.join(ROOT, "scripts/convergence.py"), "--steps", "100", "--bsp", "--strategy", strat]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, cwd=ROOT, env=e)
+        line = [l for l in r.stdout.splitlines() if l.startswith("CONVERGENCE ")]
+        assert r.returncode == 0 and line, r.stdout[-3000:]
+        curves[name] = json.loads(line[-1][len("CONVERGENCE "):])["bsp_bf16"]["curve"]
+    for name in ("fused", "fused_p2p"):
+        for a, b in zip(curves["classic"], curves[name]):
+            assert abs(a[1] - b[1]) < 0.08 + 0.1 * a[1], (name, curves)       # smoothed training loss
+            assert abs(a[2] - b[2]) < 0.08 + 0.15 * a[2], (name, curves)      # validation cost
+    assert curves["classic"][-1][1] < 0.2 * curves["classic"][0][1]             # and it actually learns

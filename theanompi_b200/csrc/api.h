@@ -32,8 +32,9 @@ struct FusedArgs {
   int pre_reduced;                                   // the range's gradients were already reduce-scattered into their owner's G by the
                                                      // wgrad GEMM epilogues (gemm_rs_*): skip the gather, zero G after use
   int push_master = 1;                               // two-shot: 1 = push the updated fp32 master slice AND the bf16 shadow to every peer;
-                                                     // 0 = owner keeps the master (peers receive only the bf16 compute shadow — a third of
-                                                     // the all-gather bytes); push_master_slices() re-synchronises W on demand
+                                                     // 0 = owner keeps the master of WEIGHT blocks (group 0): peers receive only their bf16
+                                                     // compute shadow — a third of the all-gather bytes; bias blocks (read in fp32 by the
+                                                     // forward pass) are always pushed; push_master_slices() re-synchronises W on demand
 };
 
 struct ReduceArgs {

@@ -321,7 +321,9 @@ __global__ void __launch_bounds__(kThreads) fused_twoshot_sgd_kernel(const Fused
       sgd4(w, uu, gs[u], h, a.tab.lr_mult[grp[u]], a.tab.wd[grp[u]]);
       *reinterpret_cast<float4*>(U_ + i) = uu;
       const uint2 wh = pack_bf16x4(w);
-      const bool push_w = a.push_master || a.h_off < 0;       // owner-keeps-master needs a shadow for the peers to compute with
+      // owner-keeps-master ships only the bf16 shadow — of plain WEIGHT blocks (group 0).  Biases (and anything else the
+      // forward pass reads in fp32 straight from W) always travel as fp32 masters: they are a few KB.
+      const bool push_w = a.push_master || a.h_off < 0 || grp[u] != 0;
       if (use_nvls) {
         if (push_w) mc_st_f4(reinterpret_cast<float*>(reinterpret_cast<char*>(a.ctx.mc_arena) + a.w_off) + i, w);
         else *reinterpret_cast<float4*>(W + i) = w;

@@ -85,10 +85,11 @@ class BSP_Exchanger(object):
             if gpucomm is None:
                 raise RuntimeError("strategy %s needs the symmetric peer arena (GPUs of one node)" % exch_strategy)
             self.algo, self.wire16 = FUSED[exch_strategy]
-            # owner-keeps-master (default when the model computes from bf16 shadows): the fused kernel ships only the bf16
-            # compute shadow of an updated slice to the peers — a third of the all-gather bytes; the fp32 master copies of
-            # non-owners go stale until sync_master() (called before checkpoints / by finalize).  TMPI_PUSH_MASTER=1 restores
-            # the full push.
+            # owner-keeps-master (default when the model computes from bf16 shadows): for WEIGHT tensors the fused kernel
+            # ships only the bf16 compute shadow of an updated slice to the peers — a third of the all-gather bytes; their
+            # fp32 master copies on non-owners go stale until sync_master() (called before checkpoints / by finalize).
+            # Biases — which the forward kernels read in fp32 — always travel as masters.  TMPI_PUSH_MASTER=1 restores the
+            # full push.
             self.push_master = (os.environ.get("TMPI_PUSH_MASTER", "0") == "1") or self.arena.H is None
             self._master_stale = False
             self._setup_buckets()

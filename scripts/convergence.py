@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 
-def run_one(dtype, steps, rank, size, batch, worker=None, lr=0.001):
+def run_one(dtype, steps, rank, size, batch, worker=None, lr=0.001, overlap=True, comm_blocks=0, graph=False):
     from theanompi_b200.models import layers2
     from theanompi_b200.models.cifar10 import Cifar10_model
     from theanompi_b200.utils.recorder import Recorder
@@ -27,6 +27,11 @@ def run_one(dtype, steps, rank, size, batch, worker=None, lr=0.001):
     if worker is not None:
         cfg = worker.model_config("Cifar10_model", **{k: v for k, v in cfg.items() if k not in ("rank", "size", "device", "verbose")})
         cfg["verbose"] = False
+        cfg["overlap"] = overlap
+        if comm_blocks:
+            cfg["comm_blocks"] = comm_blocks
+        if graph:
+            cfg["cuda_graph"] = True
     m = Cifar10_model(cfg)
     if worker is not None:
         worker.build(m, cfg)
@@ -61,6 +66,9 @@ def main():
     ap.add_argument("--bsp", action="store_true")
     ap.add_argument("--global-batch", type=int, default=128)
     ap.add_argument("--strategy", default="fused")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--comm-blocks", type=int, default=0)
+    ap.add_argument("--graph", action="store_true")
     a = ap.parse_args()
     rank, size = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
@@ -68,7 +76,8 @@ def main():
     if a.bsp or size > 1:
         from theanompi_b200.worker import BSP_Worker
         w = BSP_Worker("cuda%d" % int(os.environ.get("LOCAL_RANK", "0")), "cdd", a.strategy)
-        curve, verr = run_one("bf16", a.steps, rank, size, a.global_batch // size, worker=w if size > 1 else None)
+        curve, verr = run_one("bf16", a.steps, rank, size, a.global_batch // size, worker=w if size > 1 else None, overlap=not a.no_overlap,
+                              comm_blocks=a.comm_blocks, graph=a.graph)
         out["bsp_bf16"] = {"curve": curve, "val_err": verr, "strategy": a.strategy, "push_master": os.environ.get("TMPI_PUSH_MASTER", "0"),
                            "nvls": os.environ.get("TMPI_NVLS", "1")}
         if rank == 0:

@@ -188,3 +188,23 @@ def test_deterministic_mode_is_bit_reproducible():
         assert r.returncode == 0, r.stdout[-2000:]
         outs.append(torch.load(f))
     assert torch.equal(outs[0], outs[1])
+
+
+def test_label_staging_survives_a_host_that_runs_ahead():
+    """The host enqueues whole steps ahead of the device (always under CUDA graphs, and whenever a step is GPU-bound): the
+    pinned label staging must not be overwritten with the next batch before the copy of the current one has executed —
+    otherwise images and labels of consecutive steps get mixed (the 2-GPU trajectory regression this guards against)."""
+    import numpy as np
+    from theanompi_b200.models.cifar10 import Cifar10_model
+    m = Cifar10_model(dict(verbose=False, rank=0, size=1, device="cuda:0", batch_size=64, file_batch_size=64, cuda_graph=False,
+                           data_kwargs=dict(n_synthetic=256, synthetic=True)))
+    B = int(m.shared_y.shape[0])
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(4e8))                       # the device is ~0.2 s behind the host from here on
+    got = []
+    for i in range(9):
+        m._labels_to_device(np.full(B, i, dtype=np.int64))
+        got.append(m.shared_y.clone())               # stream-ordered: sees what the i-th H2D copy delivered
+    torch.cuda.synchronize()
+    for i, g in enumerate(got):
+        assert bool((g == i).all()), (i, g[:4].tolist())

@@ -55,33 +55,40 @@ __global__ void __launch_bounds__(256) bn_colreduce_kernel(const T* __restrict__
       for (int i = 0; i < N; ++i) { mu[i] = mean[cv * N + i]; rs[i] = rstd[cv * N + i]; }
     }
     const long long rend = min(R, r0 + rows_per_cta);
-    // 4 rows per trip, all loads issued before any use (this pass is pure streaming: memory-level parallelism is everything)
-    for (long long r = r0 + tr; r < rend; r += 4 * RL) {
-      float xv[4][N], gv[4][N], yv[4][N];
+    // UR rows per trip, all (raw 16-byte) loads issued before any use — this pass is pure streaming, memory-level parallelism
+    // is everything; the vectors stay packed until they are consumed so the trip fits in ~64 registers
+    constexpr int UR = MODE == 0 ? 4 : 2;
+    for (long long r = r0 + tr; r < rend; r += UR * RL) {
+      uint4 xr[UR], gr[UR], yr[UR];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UR; ++u) {
         const long long rr = r + (long long)u * RL;
         if (rr < rend) {
-          VecIO<T>::ld(x + rr * C + cv * N, xv[u]);
+          xr[u] = *reinterpret_cast<const uint4*>(x + rr * C + cv * N);
           if (MODE == 1) {
-            VecIO<T>::ld(dy + rr * C + cv * N, gv[u]);
-            if (relu) VecIO<T>::ld(y + rr * C + cv * N, yv[u]);
+            gr[u] = *reinterpret_cast<const uint4*>(dy + rr * C + cv * N);
+            if (relu) yr[u] = *reinterpret_cast<const uint4*>(y + rr * C + cv * N);
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < UR; ++u) {
         const long long rr = r + (long long)u * RL;
         if (rr < rend) {
+          float xv[N];
+          VecIO<T>::ld(reinterpret_cast<const T*>(&xr[u]), xv);
           if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < N; ++i) { a[i] += xv[u][i]; b[i] += xv[u][i] * xv[u][i]; }
+            for (int i = 0; i < N; ++i) { a[i] += xv[i]; b[i] += xv[i] * xv[i]; }
           } else {
+            float gv[N], yv[N];
+            VecIO<T>::ld(reinterpret_cast<const T*>(&gr[u]), gv);
+            if (relu) VecIO<T>::ld(reinterpret_cast<const T*>(&yr[u]), yv);
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-              float g = gv[u][i];
-              if (relu && !(yv[u][i] > 0.f)) g = 0.f;
-              a[i] += g; b[i] += g * (xv[u][i] - mu[i]) * rs[i];
+              float g = gv[i];
+              if (relu && !(yv[i] > 0.f)) g = 0.f;
+              a[i] += g; b[i] += g * (xv[i] - mu[i]) * rs[i];
             }
           }
         }

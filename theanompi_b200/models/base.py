@@ -135,7 +135,12 @@ class ModelBase(object):
         self.shared_y = torch.zeros((fb,), dtype=torch.int64, device=self.device)
         self.x_in = torch.zeros((B,) + self.input_shape[1:], dtype=self.act_dtype, device=self.device)
         self.y_in = torch.zeros((B,), dtype=torch.int64, device=self.device)
-        self._y_pinned = torch.zeros((fb,), dtype=torch.int64, pin_memory=self.cuda)
+        # label staging: a small ring of pinned buffers, each guarded by the event of its last H2D copy — the host runs
+        # ahead of the device (always under CUDA graphs, and whenever a step is GPU-bound), so a single buffer would be
+        # overwritten with the NEXT batch's labels before the copy of the current ones has executed
+        self._y_ring = [torch.zeros((fb,), dtype=torch.int64, pin_memory=self.cuda) for _ in range(4 if self.cuda else 1)]
+        self._y_ev = [None] * len(self._y_ring)
+        self._y_k = 0
         self.vels, self.vels2 = [], []
         if self.verbose:
             print("%s: %d tensors, %.3f M params, arena %.1f MiB on %s"
@@ -308,8 +313,17 @@ class ModelBase(object):
     # ------------------------------------------------------------------ data movement
     def _labels_to_device(self, labels):
         n = len(labels)
-        self._y_pinned[:n] = torch.as_tensor(np.asarray(labels, dtype=np.int64))
-        self.shared_y[:n].copy_(self._y_pinned[:n], non_blocking=True)
+        k = self._y_k
+        self._y_k = (k + 1) % len(self._y_ring)
+        if self._y_ev[k] is not None:
+            self._y_ev[k].synchronize()
+        buf = self._y_ring[k]
+        buf[:n] = torch.as_tensor(np.asarray(labels, dtype=np.int64))
+        self.shared_y[:n].copy_(buf[:n], non_blocking=True)
+        if self.cuda:
+            if self._y_ev[k] is None:
+                self._y_ev[k] = torch.cuda.Event()
+            self._y_ev[k].record(torch.cuda.current_stream(self.device))
         return n * 8
 
     def _load_file_batch(self, mode, idx, img, labels, n_batches):

@@ -137,3 +137,25 @@ def test_failfast_teardown(tmp_path, monkeypatch):
     rule.init(devices=["cpu0", "cpu1"], modelfile="theanompi_b200.models.cifar10", modelclass="NoSuchModel")
     rc = rule.proc.wait(timeout=120)
     assert rc != 0
+
+
+def test_rule_bsp_two_hosts_through_remote_shell(tmp_path, monkeypatch):
+    """The multi-host path (``host:device`` entries → one remote shell per worker, per-host LOCAL_RANK, rendezvous on the first
+    host, NCCL/gloo strategy instead of the peer-memory one): two "hosts" that both resolve to this machine, reached through a
+    local stand-in for ssh — the reference's ``mpirun -host`` MPMD launch (``rules.py:85-116``)."""
+    import stat
+    import theanompi_b200 as tm
+    monkeypatch.chdir(tmp_path)
+    shim = tmp_path / "fake_ssh"
+    log = tmp_path / "ssh_calls.log"
+    shim.write_text("#!/bin/sh\n# usage: fake_ssh HOST 'command line'\necho \"$1\" >> %s\nshift\nexec sh -c \"$*\"\n" % log)
+    shim.chmod(shim.stat().st_mode | stat.S_IXUSR)
+    monkeypatch.setenv("TMPI_SSH", str(shim))
+    monkeypatch.setenv("TMPI_MASTER_ADDR", "127.0.0.1")
+    tm.BSP.sync_type, tm.BSP.exch_strategy = "cdd", "fused"          # must fall back to a network strategy on its own
+    try:
+        assert _run_rule(tm.BSP, ["nodeA:cpu0", "nodeB:cpu0"]) == 0
+    finally:
+        tm.BSP.exch_strategy = "fused"
+    assert sorted(log.read_text().split()) == ["nodeA", "nodeB"]
+    assert os.path.exists(tmp_path / "inforec" / "inforec.pkl")

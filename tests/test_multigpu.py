@@ -86,10 +86,10 @@ def test_fused_exchange_follows_classic_trajectory():
     any rank computing with stale parameters."""
     import json
     curves = {}
-    for name, strat, env in (("classic", "nccl32", {}), ("fused", "fused", {}), ("fused_p2p", "fused", {"TMPI_NVLS": "0"})):
+    for k, (name, strat, env) in enumerate((("classic", "nccl32", {}), ("fused", "fused", {}), ("fused_p2p", "fused", {"TMPI_NVLS": "0"}))):
         e = dict(os.environ); e.update(env)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-               "--master-port", "29640", os.path.join(ROOT, "scripts/convergence.py"), "--steps", "100", "--bsp", "--strategy", strat]
+               "--master-port", str(29640 + k), os.path.join(ROOT, "scripts/convergence.py"), "--steps", "100", "--bsp", "--strategy", strat]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, cwd=ROOT, env=e)
         line = [l for l in r.stdout.splitlines() if l.startswith("CONVERGENCE ")]
         assert r.returncode == 0 and line, r.stdout[-3000:]

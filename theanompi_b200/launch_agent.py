@@ -6,7 +6,8 @@ contract: it starts every worker in its own process group with the torch.distrib
 rendezvous environment (``RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR / MASTER_PORT``),
 waits, and on the first non-zero exit (or SIGTERM/SIGINT) kills all remaining worker
 groups (loader children included).  Remote hosts are reached with ``ssh`` like the
-reference's ``-host`` MPMD entries.
+reference's ``-host`` MPMD entries (``TMPI_SSH`` overrides the remote-shell command, default
+``ssh -o BatchMode=yes``; the multi-host test points it at a local shim).
 """
 from __future__ import annotations
 
@@ -64,7 +65,8 @@ def main():
             extra = " ".join("%s=%s" % (k, shlex.quote(v)) for k, v in spec.get("env", {}).items())
             remote = "cd %s && env %s %s %s" % (shlex.quote(spec.get("cwd", ".")), exports, extra,
                                                 " ".join(shlex.quote(c) for c in cmd))
-            p = subprocess.Popen(["ssh", "-o", "BatchMode=yes", host, remote], start_new_session=True)
+            rsh = shlex.split(os.environ.get("TMPI_SSH", "ssh -o BatchMode=yes"))
+            p = subprocess.Popen(rsh + [host, remote], start_new_session=True)
         procs.append(p)
 
     rc = 0

@@ -62,6 +62,7 @@ class Rule(object):
         first = hosts[0]
         master = "127.0.0.1" if all(h in (None, first) for h in hosts) and first in (None, "localhost", socket.gethostname()) \
             else (first or socket.gethostname())
+        master = os.environ.get("TMPI_MASTER_ADDR", master)         # e.g. a host name that differs on the fabric network
         port = int(os.environ.get("TMPI_MASTER_PORT", _free_port()))
         workers = []
         for rank, (device, module, argv) in enumerate(programs):

@@ -141,7 +141,8 @@ def reference_arm(args):
                    "are not in the offline wheelhouse and the code is Python-2 era" % ",".join(missing))
     if why is None:
         why = "reference import unexpectedly succeeded but no runnable stock path is wired"
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
     return 0
 
 

@@ -260,6 +260,12 @@ def test_hwloc_utils():
     assert aff[0].startswith("0-55") and aff[1] == "56-111"
     used = h.bind_to_socket_mem(",".join(str(c) for c in sorted(os.sched_getaffinity(0))), label="t")
     assert used and os.environ["CPULIST_t"]
+    # explicit memory binding (the reference's set_membind): policy visible in /proc/self/numa_maps-independent way —
+    # get_mempolicy is not wrapped, so check the syscall result and that resetting works
+    nodes = h.nodes_of_cpus(used)
+    if nodes and h.set_membind(nodes[:1]):
+        assert h.set_membind([], h.MPOL_DEFAULT)
+    assert h.set_membind([], h.MPOL_BIND) is False           # an empty node set is refused, nothing changes
 
 
 def test_data_extend_shuffle_shard():

@@ -396,3 +396,19 @@ def test_arena_buckets_with_solo_parameters():
     for a, b in zip(bs, bs[1:]):
         assert a["lo"] == b["hi"]
     assert all(b["lo"] % 1024 == 0 and b["hi"] % 1024 == 0 for b in bs)
+
+
+def test_parallel_copyto_matches_copyto(tmp_path, monkeypatch):
+    from theanompi_b200.models.data.utils import parallel_copyto
+    rs = np.random.RandomState(3)
+    src = rs.randint(0, 256, (37, 64, 64, 3), dtype=np.uint8)
+    f = tmp_path / "b.npy"
+    np.save(f, src)
+    for threads in (1, 3, 8):
+        out = np.zeros_like(src)
+        parallel_copyto(out, np.load(f, mmap_mode="r"), threads=threads, min_bytes=0)
+        assert np.array_equal(out, src)
+    monkeypatch.setenv("TMPI_LOADER_THREADS", "2")
+    out = np.zeros_like(src)
+    parallel_copyto(out, src, min_bytes=0)
+    assert np.array_equal(out, src)

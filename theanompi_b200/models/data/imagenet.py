@@ -106,8 +106,9 @@ class ImageNet_data(object):
                 arr = np.transpose(arr, (3, 1, 2, 0))
             np.copyto(out, arr.astype(np.uint8, copy=False))
         else:
+            from .utils import parallel_copyto
             arr = np.load(filename, mmap_mode="r")
-            np.copyto(out, arr)
+            parallel_copyto(out, arr)
 
     # ------------------------------------------------------------------ batching / sharding
     def batch_data(self, file_batch_size):

@@ -35,8 +35,9 @@ def read_batch_file(filename, out, n_channels=3):
             arr = np.transpose(arr, (3, 1, 2, 0))
         np.copyto(out, arr.astype(np.uint8, copy=False))
     else:
+        from .utils import parallel_copyto
         arr = np.load(filename, mmap_mode="r")
-        np.copyto(out, arr)
+        parallel_copyto(out, arr)
 
 
 def _synthetic_fill(filename, out, seed):

@@ -9,9 +9,34 @@ one pass after the pinned H2D copy.
 """
 from __future__ import annotations
 
+import os
 import pickle
 
 import numpy as np
+
+_COPY_POOL = None
+
+
+def parallel_copyto(out, src, threads=None, min_bytes=4 << 20):
+    """``np.copyto(out, src)`` split over a few threads along the first axis.  One core moves a 25 MB file batch out of the
+    page cache at 4–6 GB/s (≈ 4–6 ms) — slower than a B200 consumes it (AlexNet-128b: one batch per 1.6 ms), so the host copy of
+    the loader can be spread over ``TMPI_LOADER_THREADS`` cores (default 1; numpy releases the GIL inside each slice copy).  On
+    the 8-vCPU build sandbox this does not help (one core already saturates its memory bandwidth, ``profiles/loader_host.md``);
+    it is meant for real hosts."""
+    global _COPY_POOL
+    n = int(threads or os.environ.get("TMPI_LOADER_THREADS", "1"))
+    n = max(1, min(n, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else n, int(out.shape[0]) if out.ndim else 1))
+    if n == 1 or out.nbytes < min_bytes:
+        np.copyto(out, src)
+        return
+    if _COPY_POOL is None or _COPY_POOL._max_workers < n:
+        from concurrent.futures import ThreadPoolExecutor
+        _COPY_POOL = ThreadPoolExecutor(max_workers=n, thread_name_prefix="tmpi-copy")
+    rows = int(out.shape[0])
+    step = (rows + n - 1) // n
+    futs = [_COPY_POOL.submit(np.copyto, out[a:a + step], src[a:a + step]) for a in range(0, rows, step)]
+    for f in futs:
+        f.result()
 
 
 def unpickle(path):

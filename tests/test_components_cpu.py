@@ -412,3 +412,36 @@ def test_parallel_copyto_matches_copyto(tmp_path, monkeypatch):
     out = np.zeros_like(src)
     parallel_copyto(out, src, min_bytes=0)
     assert np.array_equal(out, src)
+
+
+@pytest.mark.parametrize("modelfile,modelclass,cfg,steps", [
+    ("theanompi_b200.models.keras_model_zoo.wresnet", "Wide_ResNet",
+     dict(batch_size=8, file_batch_size=8, depth=10, widen=1, data_kwargs=dict(n_synthetic=64, synthetic=True)), 2),
+    ("theanompi_b200.models.lstm", "LSTM", dict(dim_proj=32, batch_size=8, data_kwargs=dict(n_synthetic=64, n_words=200)), 2),
+    ("theanompi_b200.models.lasagne_model_zoo.resnet50", "ResNet50",
+     dict(batch_size=2, file_batch_size=2, n_class=8, data_kwargs=dict(n_train_files=2, n_val_files=1, synthetic=True)), 1),
+    ("theanompi_b200.models.lasagne_model_zoo.wgan", "WGAN", dict(critic_runs=1, data_kwargs=dict(n_synthetic=128)), 2),
+    ("theanompi_b200.models.lasagne_model_zoo.lsgan", "LSGAN", dict(data_kwargs=dict(n_synthetic=128)), 2),
+])
+def test_zoo_models_step_on_the_cpu_reference_path(modelfile, modelclass, cfg, steps):
+    """The native residual / recurrent models (BN, residual add, flat Adam, LSTM sequence node) and the GAN adapters run the same
+    model code on the fp32 PyTorch reference ops when there is no GPU: a few steps train and validate."""
+    import importlib
+    import math
+    from theanompi_b200.models import layers2
+    from theanompi_b200.utils.recorder import Recorder
+    layers2.reseed(); layers2.Dropout.layers.clear(); layers2.Crop.layers.clear()
+    base = dict(verbose=False, rank=0, size=1, device="cpu")
+    base.update(cfg)
+    m = getattr(importlib.import_module(modelfile), modelclass)(base)
+    m.compile_iter_fns("avg")
+    rec = Recorder(None, 10 ** 6, modelclass, False, device="cpu")
+    w0 = m.arena.W.clone()
+    c = 0
+    for _ in range(steps):
+        out = m.train_iter(c, rec)
+        c = out if isinstance(out, int) else c + 1
+    m.val_iter(c, rec)
+    assert math.isfinite(float(rec.train_info["cost"][-1]))
+    assert not torch.equal(w0, m.arena.W), "weights did not move"
+    m.cleanup()

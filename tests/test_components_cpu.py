@@ -445,3 +445,37 @@ def test_zoo_models_step_on_the_cpu_reference_path(modelfile, modelclass, cfg, s
     assert math.isfinite(float(rec.train_info["cost"][-1]))
     assert not torch.equal(w0, m.arena.W), "weights did not move"
     m.cleanup()
+
+
+def test_arena_buckets_partition_property():
+    """Whatever the tensor sizes, bucket size, tail size and solo set: the buckets tile the arena exactly once, in reverse layer
+    order (bucket 0 = last parameters), contiguous, with every parameter in exactly one bucket — the fused exchange launches one
+    kernel per bucket over [lo, hi) and counts grad-ready callbacks per bucket, so a gap or an overlap would silently skip or
+    double-apply an update."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(sizes=st.lists(st.integers(1, 9000), min_size=1, max_size=14),
+           bucket_kb=st.integers(1, 96), tail_kb=st.integers(0, 64), solo_seed=st.integers(0, 2 ** 16))
+    def prop(sizes, bucket_kb, tail_kb, solo_seed):
+        params = [torch.zeros(s) for s in sizes]
+        a = FlatArena(params, ["W"] * len(params), "cpu")
+        rs = np.random.RandomState(solo_seed)
+        solo = set(int(i) for i in np.nonzero(rs.rand(len(sizes)) < 0.2)[0])
+        buckets = a.make_buckets(bucket_kb << 10, solo=solo, tail_bytes=tail_kb << 10)
+        assert buckets[0]["hi"] == a.numel and buckets[-1]["lo"] == 0
+        seen = []
+        for prev, b in zip([None] + buckets[:-1], buckets):
+            assert b["lo"] < b["hi"]
+            if prev is not None:
+                assert b["hi"] == prev["lo"]                                  # contiguous, descending
+            assert b["lo"] == a.offsets[b["params"][0]]
+            assert b["params"] == list(range(b["params"][0], b["params"][-1] + 1))
+            end = a.offsets[b["params"][-1] + 1] if b["params"][-1] + 1 < len(sizes) else a.numel
+            assert b["hi"] == end
+            if set(b["params"]) & solo:
+                assert len(b["params"]) == 1
+            seen.extend(b["params"])
+        assert sorted(seen) == list(range(len(sizes)))
+
+    prop()
